@@ -1,0 +1,1458 @@
+// hmgpu.cu — C ABI (include/hmgpu.h) over the sm_100a kernels in kernels.cuh.
+//
+// Host-side responsibilities, mirroring the reference's thin layers L1-L3:
+//   - Parameters / key containers and their byte formats      reference src/context.rs
+//   - per-key constants (subset tables, decrypt vector, remainder folding tables)
+//   - batch bookkeeping (slot widths + degree bounds) and circuit planning
+// All polynomial arithmetic on batches runs on the GPU; there is no CPU fallback.
+#include "../../include/hmgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "gf2host.hpp"
+#include "kernels.cuh"
+
+using hmk::Layout;
+using hmk::MulOp;
+using hmk::View;
+
+// ------------------------------------------------------------------------------------------
+struct hm_batch {
+    hm_context *ctx = nullptr;
+    size_t n = 0;
+    uint32_t L = 0;
+    std::vector<uint32_t> w;    // slot widths, u64 words
+    std::vector<uint32_t> off;  // L+1 prefix sums
+    std::vector<uint64_t> degb; // per-slot degree bound (>= true degree of every polynomial in the slot)
+    size_t value_words = 0;
+    uint64_t *d = nullptr;
+};
+
+struct hm_context {
+    uint16_t d = 0, dp = 0, delta = 0, tau = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    std::string last_error;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+
+    // secret key and what is derived from it
+    bool has_sk = false;
+    gf2::words S;
+    size_t ds = 0; // true degree of S
+    gf2::words v_host;
+    size_t v_bits = 0;
+    uint64_t *d_v = nullptr; // decrypt vector on device, v_bits bits
+    std::vector<uint32_t> vv_layout_key;
+    uint64_t *d_vv = nullptr;
+    size_t d_vv_words = 0;
+    uint32_t *d_remT = nullptr; // folding tables (ds % 32 == 0)
+    uint32_t *d_S32 = nullptr;  // S as u32 words (generic remainder)
+
+    // public key and what is derived from it
+    bool has_pk = false;
+    size_t fresh_deg = 0; // max degree over the T_i (== d+dp for generated keys)
+    uint32_t wf = 0;      // u64 words of a fresh slot
+    uint32_t enc_wb = 0, enc_groups = 0, enc_table_words = 0;
+    bool enc_table_in_smem = false;
+    uint64_t *d_enc_table = nullptr;
+
+    // scratch for op descriptors
+    MulOp *d_ops = nullptr;
+    size_t d_ops_cap = 0;
+};
+
+namespace {
+
+int fail_cuda(hm_context *ctx, cudaError_t e, const char *what) {
+    if (ctx) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        ctx->last_error = buf;
+    }
+    return HM_ERR_CUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
+    } while (0)
+
+int use_device(hm_context *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    return HM_OK;
+}
+#define USE_DEV(ctx)                    \
+    do {                                \
+        int rc__ = use_device(ctx);     \
+        if (rc__ != HM_OK) return rc__; \
+    } while (0)
+
+void zero_free_device(hm_context *ctx, void *p, size_t bytes) {
+    if (!p) return;
+    if (bytes) cudaMemsetAsync(p, 0, bytes, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(p);
+}
+
+Layout make_layout(const hm_batch *b) {
+    Layout l;
+    l.L = b->L;
+    l.value_words = (uint32_t)b->value_words;
+    for (uint32_t k = 0; k <= b->L; ++k) l.off[k] = b->off[k];
+    return l;
+}
+
+hm_batch *new_batch(hm_context *ctx, size_t n, uint32_t L, const uint64_t *degb) {
+    hm_batch *b = new (std::nothrow) hm_batch;
+    if (!b) return nullptr;
+    b->ctx = ctx;
+    b->n = n;
+    b->L = L;
+    b->w.resize(L);
+    b->off.resize(L + 1);
+    b->degb.assign(degb, degb + L);
+    uint64_t o = 0;
+    for (uint32_t k = 0; k < L; ++k) {
+        b->off[k] = (uint32_t)o;
+        b->w[k] = (uint32_t)(degb[k] / 64 + 1);
+        o += b->w[k];
+    }
+    b->off[L] = (uint32_t)o;
+    b->value_words = o;
+    return b;
+}
+
+int alloc_batch(hm_context *ctx, hm_batch *b) {
+    const size_t bytes = std::max<size_t>(b->n * b->value_words * 8, 16);
+    CK(cudaMalloc(&b->d, bytes));
+    return HM_OK;
+}
+
+int grid_for(hm_context *ctx, uint64_t work_items, int threads, int per_sm) {
+    uint64_t blocks = (work_items + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)ctx->sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int post_launch(hm_context *ctx, const char *what) {
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, what);
+    return HM_OK;
+}
+#define LAUNCHED(what)                        \
+    do {                                      \
+        int rc__ = post_launch(ctx, what);    \
+        if (rc__ != HM_OK) return rc__;       \
+    } while (0)
+
+// ---- per-key constants ---------------------------------------------------------------------
+
+int ensure_decrypt_vector(hm_context *ctx, size_t nbits) {
+    if (ctx->d_v && ctx->v_bits >= nbits) return HM_OK;
+    size_t want = std::max<size_t>(nbits, 1024);
+    ctx->v_host = gf2::decrypt_vector(ctx->S, ctx->ds, want);
+    if (ctx->d_v) zero_free_device(ctx, ctx->d_v, (ctx->v_bits + 63) / 64 * 8);
+    ctx->d_v = nullptr;
+    CK(cudaMalloc(&ctx->d_v, ctx->v_host.size() * 8));
+    CK(cudaMemcpyAsync(ctx->d_v, ctx->v_host.data(), ctx->v_host.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->v_bits = want;
+    ctx->vv_layout_key.clear();
+    return HM_OK;
+}
+
+// vv: the decrypt vector laid out like one value of the batch.
+int ensure_vv(hm_context *ctx, const hm_batch *b) {
+    size_t maxbits = 0;
+    for (uint32_t k = 0; k < b->L; ++k) maxbits = std::max<size_t>(maxbits, (size_t)b->w[k] * 64);
+    int rc = ensure_decrypt_vector(ctx, maxbits);
+    if (rc != HM_OK) return rc;
+    if (ctx->d_vv && ctx->vv_layout_key == b->w) return HM_OK;
+    std::vector<uint64_t> vv(b->value_words);
+    for (uint32_t k = 0; k < b->L; ++k)
+        for (uint32_t j = 0; j < b->w[k]; ++j) vv[b->off[k] + j] = ctx->v_host[j];
+    if (ctx->d_vv_words < vv.size()) {
+        if (ctx->d_vv) zero_free_device(ctx, ctx->d_vv, ctx->d_vv_words * 8);
+        ctx->d_vv = nullptr;
+        CK(cudaMalloc(&ctx->d_vv, vv.size() * 8));
+        ctx->d_vv_words = vv.size();
+    }
+    CK(cudaMemcpyAsync(ctx->d_vv, vv.data(), vv.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::fill(vv.begin(), vv.end(), 0);
+    ctx->vv_layout_key = b->w;
+    return HM_OK;
+}
+
+void clear_secret(hm_context *ctx) {
+    if (ctx->d_v) zero_free_device(ctx, ctx->d_v, (ctx->v_bits + 63) / 64 * 8 + 8);
+    if (ctx->d_vv) zero_free_device(ctx, ctx->d_vv, ctx->d_vv_words * 8);
+    if (ctx->d_remT) zero_free_device(ctx, ctx->d_remT, 4 * 256 * (ctx->ds / 32) * 4);
+    if (ctx->d_S32) zero_free_device(ctx, ctx->d_S32, (ctx->ds / 32 + 2) * 4);
+    ctx->d_v = ctx->d_vv = nullptr;
+    ctx->d_remT = ctx->d_S32 = nullptr;
+    ctx->d_vv_words = 0;
+    ctx->v_bits = 0;
+    // volatile-style wipe of host copies (reference src/polynomial.rs:379-401)
+    volatile uint64_t *p = ctx->S.data();
+    for (size_t i = 0; i < ctx->S.size(); ++i) p[i] = 0;
+    volatile uint64_t *q = ctx->v_host.data();
+    for (size_t i = 0; i < ctx->v_host.size(); ++i) q[i] = 0;
+    ctx->S.clear();
+    ctx->v_host.clear();
+    ctx->vv_layout_key.clear();
+    ctx->has_sk = false;
+    ctx->ds = 0;
+}
+
+void clear_public(hm_context *ctx) {
+    if (ctx->d_enc_table) cudaFree(ctx->d_enc_table);
+    ctx->d_enc_table = nullptr;
+    ctx->has_pk = false;
+    ctx->enc_table_words = 0;
+}
+
+int ensure_ops(hm_context *ctx, size_t n_ops) {
+    if (ctx->d_ops_cap >= n_ops) return HM_OK;
+    if (ctx->d_ops) cudaFree(ctx->d_ops);
+    ctx->d_ops = nullptr;
+    size_t cap = std::max<size_t>(n_ops, 256);
+    CK(cudaMalloc(&ctx->d_ops, cap * sizeof(MulOp)));
+    ctx->d_ops_cap = cap;
+    return HM_OK;
+}
+
+// ---- kernel launch wrappers --------------------------------------------------------------------
+
+int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops, size_t n) {
+    if (ops.empty() || n == 0) return HM_OK;
+    int rc = ensure_ops(ctx, ops.size());
+    if (rc != HM_OK) return rc;
+    // stream-ordered: descriptors are copied before the kernel that reads them; the host vector
+    // must stay alive until the copy is done, so synchronise the copy (tiny).
+    CK(cudaMemcpyAsync(ctx->d_ops, ops.data(), ops.size() * sizeof(MulOp), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint32_t per_warp = 0;
+    for (const MulOp &o : ops) per_warp = std::max(per_warp, 2 * (o.a.w + o.b.w));
+    per_warp = (per_warp + 3) & ~3u;
+    const size_t smem = (size_t)per_warp * 4 * hmk::MUL_WARPS;
+    if (smem > ctx->smem_optin) return HM_ERR_UNSUPPORTED;
+    CK(cudaFuncSetAttribute(hmk::mul_views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // gridDim.y is limited to 65535 ops per launch
+    for (size_t first = 0; first < ops.size(); first += 65535) {
+        const size_t cnt = std::min<size_t>(65535, ops.size() - first);
+        dim3 grid((unsigned)((n + hmk::MUL_WARPS - 1) / hmk::MUL_WARPS), (unsigned)cnt);
+        hmk::mul_views_kernel<<<grid, hmk::MUL_WARPS * 32, smem, ctx->stream>>>(ctx->d_ops + first, n, per_warp);
+        LAUNCHED("mul_views_kernel");
+    }
+    return HM_OK;
+}
+
+int launch_xor_views(hm_context *ctx, View o, View a, View b, size_t n) {
+    if (n == 0) return HM_OK;
+    const int grid = grid_for(ctx, (uint64_t)n * o.w, 256, 16);
+    hmk::xor_views_kernel<<<grid, 256, 0, ctx->stream>>>(o, a, b, n);
+    LAUNCHED("xor_views_kernel");
+    return HM_OK;
+}
+
+int launch_rem(hm_context *ctx, View a, View o, size_t n) {
+    if (n == 0) return HM_OK;
+    const size_t ds = ctx->ds;
+    const bool fold = (ds % 32 == 0) && (ds / 32 == 2 || ds / 32 == 4 || ds / 32 == 8 || ds / 32 == 16);
+    if (fold) {
+        const int ws = (int)(ds / 32);
+        const size_t smem = (size_t)4 * 256 * ws * 4;
+        const unsigned grid = (unsigned)((n + 127) / 128);
+#define REM_CASE(WS)                                                                                                  \
+    case WS:                                                                                                          \
+        CK(cudaFuncSetAttribute(hmk::rem_fold_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        hmk::rem_fold_kernel<WS><<<grid, 128, smem, ctx->stream>>>(a, o, n, ctx->d_remT);                             \
+        break;
+        switch (ws) {
+            REM_CASE(2)
+            REM_CASE(4)
+            REM_CASE(8)
+            REM_CASE(16)
+        }
+#undef REM_CASE
+        LAUNCHED("rem_fold_kernel");
+        return HM_OK;
+    }
+    uint32_t per_warp = (2 * a.w + 1 + 3) & ~3u;
+    const size_t smem = (size_t)per_warp * 4 * hmk::MUL_WARPS;
+    if (smem > ctx->smem_optin) return HM_ERR_UNSUPPORTED;
+    CK(cudaFuncSetAttribute(hmk::rem_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((n + hmk::MUL_WARPS - 1) / hmk::MUL_WARPS);
+    hmk::rem_generic_kernel<<<grid, hmk::MUL_WARPS * 32, smem, ctx->stream>>>(a, o, n, ctx->d_S32, (uint32_t)ds, per_warp);
+    LAUNCHED("rem_generic_kernel");
+    return HM_OK;
+}
+
+View slot_view(const hm_batch *b, uint32_t k) {
+    View v;
+    v.base = b->d;
+    v.stride = b->value_words;
+    v.off = b->off[k];
+    v.w = b->w[k];
+    return v;
+}
+View null_view() {
+    View v;
+    v.base = nullptr;
+    v.stride = 0;
+    v.off = 0;
+    v.w = 0;
+    return v;
+}
+
+bool same_layout(const hm_batch *a, const hm_batch *b) { return a->L == b->L && a->w == b->w; }
+
+int xor_batches(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
+    if (a->n == 0) return HM_OK;
+    if (same_layout(a, b) && same_layout(a, o)) {
+        const uint64_t total = (uint64_t)a->n * a->value_words;
+        const uint64_t n16 = total / 2;
+        if (n16) {
+            const int grid = grid_for(ctx, n16, 256, 16);
+            hmk::xor_flat_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(a->d),
+                                                                 reinterpret_cast<const uint4 *>(b->d),
+                                                                 reinterpret_cast<uint4 *>(o->d), n16);
+            LAUNCHED("xor_flat_kernel");
+        }
+        if (total & 1) {
+            hmk::xor_flat_tail_kernel<<<1, 32, 0, ctx->stream>>>(a->d, b->d, o->d, n16 * 2, total);
+            LAUNCHED("xor_flat_tail_kernel");
+        }
+        return HM_OK;
+    }
+    const int grid = grid_for(ctx, (uint64_t)o->n * o->value_words, 256, 16);
+    hmk::xor_layout_kernel<<<grid, 256, 0, ctx->stream>>>(a->d, make_layout(a), b->d, make_layout(b), o->d, make_layout(o),
+                                                           o->n);
+    LAUNCHED("xor_layout_kernel");
+    return HM_OK;
+}
+
+// ---- circuit planning on an arena of per-value polynomials ------------------------------------
+struct PolyRef {
+    uint64_t *base;
+    uint64_t stride;
+    uint32_t off;
+    uint32_t w_alloc;
+    uint64_t degb;
+    bool zero; // known to be the null polynomial for every value
+    View view() const {
+        View v;
+        v.base = base;
+        v.stride = stride;
+        v.off = off;
+        v.w = zero ? 1u : (uint32_t)std::min<uint64_t>(w_alloc, degb / 64 + 1);
+        return v;
+    }
+};
+
+} // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char *hm_status_string(int s) {
+    switch (s) {
+        case HM_OK: return "ok";
+        case HM_ERR_INVALID_PARAMETERS: return "invalid parameters (d, dp, delta, tau must be > 0 and delta < d)";
+        case HM_ERR_PUBLIC_KEY_UNSET: return "public key unset";
+        case HM_ERR_SECRET_KEY_UNSET: return "secret key unset";
+        case HM_ERR_OPERATION_REQUIREMENT: return "operation requirement not met (d < MIN_D_OVER_DELTA * delta)";
+        case HM_ERR_INVALID_LENGTH: return "invalid ciphered length (not a multiple of 8 bits)";
+        case HM_ERR_CUDA: return "CUDA error or no CUDA device";
+        case HM_ERR_UNSUPPORTED: return "shape not supported by the kernels";
+        case HM_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case HM_ERR_DIVIDE_BY_ZERO: return "attempt to divide by zero";
+        default: return "unknown status";
+    }
+}
+
+const char *hm_last_error(const hm_context *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int hm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int hm_context_create(uint16_t d, uint16_t dp, uint16_t delta, uint16_t tau, int device, hm_context **out) {
+    if (!out) return HM_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    // Parameters::new asserts, reference src/context.rs:87-94
+    if (d == 0 || dp == 0 || delta == 0 || tau == 0 || delta >= d) return HM_ERR_INVALID_PARAMETERS;
+    if (device < 0 || device >= hm_device_count()) return HM_ERR_CUDA;
+    hm_context *ctx = new (std::nothrow) hm_context;
+    if (!ctx) return HM_ERR_INVALID_ARGUMENT;
+    ctx->d = d;
+    ctx->dp = dp;
+    ctx->delta = delta;
+    ctx->tau = tau;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return HM_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    }
+    *out = ctx;
+    return HM_OK;
+}
+
+void hm_context_destroy(hm_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    clear_secret(ctx);
+    clear_public(ctx);
+    if (ctx->d_ops) cudaFree(ctx->d_ops);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int hm_context_parameters(const hm_context *ctx, uint16_t *d, uint16_t *dp, uint16_t *delta, uint16_t *tau) {
+    if (!ctx) return HM_ERR_INVALID_ARGUMENT;
+    if (d) *d = ctx->d;
+    if (dp) *dp = ctx->dp;
+    if (delta) *delta = ctx->delta;
+    if (tau) *tau = ctx->tau;
+    return HM_OK;
+}
+
+int hm_context_set_stream(hm_context *ctx, void *cuda_stream) {
+    if (!ctx) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return HM_OK;
+}
+void *hm_context_stream(const hm_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int hm_context_synchronize(hm_context *ctx) {
+    if (!ctx) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HM_OK;
+}
+uint64_t hm_context_kernel_launches(const hm_context *ctx) { return ctx ? ctx->launches : 0; }
+int hm_context_device(const hm_context *ctx) { return ctx ? ctx->device : -1; }
+
+// ---- keys -------------------------------------------------------------------------------------
+static gf2::words words_from_bytes(const uint8_t *bytes, size_t len) { // Polynomial::from_bytes, polynomial.rs:108-122
+    gf2::words w((len + 7) / 8, 0);
+    for (size_t i = 0; i < len; ++i) w[i / 8] |= (uint64_t)bytes[i] << (8 * (i % 8));
+    return w;
+}
+
+int hm_set_secret_key(hm_context *ctx, const uint8_t *bytes, size_t len) {
+    if (!ctx || !bytes || len == 0) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    gf2::words S = words_from_bytes(bytes, len);
+    if (gf2::is_zero(S.data(), S.size())) return HM_ERR_DIVIDE_BY_ZERO; // rem would panic, polynomial.rs:319-322
+    const size_t ds = gf2::degree(S.data(), S.size());
+    if (ds == 0) return HM_ERR_INVALID_ARGUMENT; // S = 1: the reference's rem never terminates
+    clear_secret(ctx);
+    clear_public(ctx); // Context::set_secret_key clears the public key, context.rs:568-571
+    S.resize(ds / 64 + 1);
+    ctx->S = S;
+    ctx->ds = ds;
+    ctx->has_sk = true;
+    // S as u32 words for the generic remainder kernel
+    std::vector<uint32_t> s32(ds / 32 + 2, 0);
+    for (size_t i = 0; i < ds / 32 + 1; ++i) s32[i] = (uint32_t)(S[i / 2] >> (32 * (i % 2)));
+    CK(cudaMalloc(&ctx->d_S32, s32.size() * 4));
+    CK(cudaMemcpyAsync(ctx->d_S32, s32.data(), s32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ds % 32 == 0) {
+        std::vector<uint32_t> T = gf2::rem_fold_tables(S, ds);
+        CK(cudaMalloc(&ctx->d_remT, T.size() * 4));
+        CK(cudaMemcpyAsync(ctx->d_remT, T.data(), T.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::fill(T.begin(), T.end(), 0);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::fill(s32.begin(), s32.end(), 0);
+    return HM_OK;
+}
+
+int hm_set_public_key(hm_context *ctx, const uint8_t *const *polys, const size_t *lens, size_t n_polys) {
+    if (!ctx || !polys || !lens) return HM_ERR_INVALID_ARGUMENT;
+    if (n_polys != ctx->tau) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    std::vector<gf2::words> T(n_polys);
+    size_t maxdeg = 0;
+    for (size_t i = 0; i < n_polys; ++i) {
+        if (!polys[i] || lens[i] == 0) return HM_ERR_INVALID_ARGUMENT;
+        T[i] = words_from_bytes(polys[i], lens[i]);
+        maxdeg = std::max(maxdeg, gf2::degree(T[i].data(), T[i].size()));
+    }
+    clear_public(ctx);
+    ctx->fresh_deg = maxdeg;
+    ctx->wf = (uint32_t)(maxdeg / 64 + 1);
+    const uint32_t wf = ctx->wf, tau = ctx->tau;
+    // window: largest of 8/4/2/1 whose table (+ staging) fits in shared memory
+    const size_t budget = ctx->smem_optin > 48 * 1024 ? ctx->smem_optin - 44 * 1024 : 0;
+    uint32_t wb = 1;
+    bool in_smem = false;
+    for (uint32_t cand : {8u, 4u, 2u, 1u}) {
+        const size_t groups = (tau + cand - 1) / cand;
+        const size_t bytes = groups * ((size_t)1 << cand) * wf * 8;
+        if (bytes <= budget) {
+            wb = cand;
+            in_smem = true;
+            break;
+        }
+    }
+    if (!in_smem) wb = 4; // table stays in global memory / L2
+    const uint32_t groups = (tau + wb - 1) / wb;
+    std::vector<uint64_t> tab((size_t)groups * ((size_t)1 << wb) * wf, 0);
+    for (uint32_t g = 0; g < groups; ++g)
+        for (uint32_t e = 1; e < (1u << wb); ++e) {
+            const uint32_t low = e & (~e + 1u);      // lowest set bit
+            const uint32_t bit = __builtin_ctz(low); // its index
+            const uint32_t i = g * wb + bit;         // public polynomial index
+            uint64_t *row = &tab[((size_t)(g << wb) + e) * wf];
+            const uint64_t *prev = &tab[((size_t)(g << wb) + (e ^ low)) * wf];
+            for (uint32_t j = 0; j < wf; ++j) row[j] = prev[j];
+            if (i < tau) // mask bits >= tau are never looked at by the reference (cipher.rs:105)
+                for (uint32_t j = 0; j < wf && j < T[i].size(); ++j) row[j] ^= T[i][j];
+        }
+    CK(cudaMalloc(&ctx->d_enc_table, tab.size() * 8));
+    CK(cudaMemcpyAsync(ctx->d_enc_table, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->enc_wb = wb;
+    ctx->enc_groups = groups;
+    ctx->enc_table_words = (uint32_t)tab.size();
+    ctx->enc_table_in_smem = in_smem;
+    ctx->has_pk = true;
+    return HM_OK;
+}
+
+int hm_has_secret_key(const hm_context *ctx) { return ctx && ctx->has_sk; }
+int hm_has_public_key(const hm_context *ctx) { return ctx && ctx->has_pk; }
+
+// ---- batches ----------------------------------------------------------------------------------
+size_t hm_batch_len(const hm_batch *b) { return b ? b->n : 0; }
+uint32_t hm_batch_bits(const hm_batch *b) { return b ? b->L : 0; }
+size_t hm_batch_value_words(const hm_batch *b) { return b ? b->value_words : 0; }
+int hm_batch_slot_words(const hm_batch *b, uint32_t *widths_out) {
+    if (!b || !widths_out) return HM_ERR_INVALID_ARGUMENT;
+    for (uint32_t k = 0; k < b->L; ++k) widths_out[k] = b->w[k];
+    return HM_OK;
+}
+int hm_batch_slot_degree_bounds(const hm_batch *b, uint64_t *bounds_out) {
+    if (!b || !bounds_out) return HM_ERR_INVALID_ARGUMENT;
+    for (uint32_t k = 0; k < b->L; ++k) bounds_out[k] = b->degb[k];
+    return HM_OK;
+}
+void *hm_batch_device_ptr(const hm_batch *b) { return b ? (void *)b->d : nullptr; }
+
+void hm_batch_free(hm_context *ctx, hm_batch *b) {
+    if (!b) return;
+    if (!ctx) ctx = b->ctx;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (b->d) cudaFree(b->d);
+    delete b;
+}
+
+int hm_batch_upload_bounded(hm_context *ctx, size_t n, uint32_t L, const uint64_t *degree_bounds, const uint64_t *host,
+                            hm_batch **out) {
+    if (!ctx || !out || !degree_bounds || (!host && n) || L == 0 || L > (uint32_t)hmk::MAX_SLOTS)
+        return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    hm_batch *b = new_batch(ctx, n, L, degree_bounds);
+    if (!b) return HM_ERR_INVALID_ARGUMENT;
+    int rc = alloc_batch(ctx, b);
+    if (rc != HM_OK) {
+        delete b;
+        return rc;
+    }
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(b->d, host, n * b->value_words * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            hm_batch_free(ctx, b);
+            return fail_cuda(ctx, e, "upload");
+        }
+    }
+    *out = b;
+    return HM_OK;
+}
+
+int hm_batch_upload(hm_context *ctx, size_t n, uint32_t L, const uint32_t *slot_words, const uint64_t *host,
+                    hm_batch **out) {
+    if (!slot_words || L == 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
+    std::vector<uint64_t> degb(L);
+    for (uint32_t k = 0; k < L; ++k) {
+        if (slot_words[k] == 0) return HM_ERR_INVALID_ARGUMENT; // empty polynomial, polynomial.rs:54-57
+        degb[k] = (uint64_t)slot_words[k] * 64 - 1;
+    }
+    return hm_batch_upload_bounded(ctx, n, L, degb.data(), host, out);
+}
+
+int hm_batch_download(hm_context *ctx, const hm_batch *b, uint64_t *host) {
+    if (!ctx || !b || (!host && b->n)) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    if (b->n) CK(cudaMemcpyAsync(host, b->d, b->n * b->value_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HM_OK;
+}
+
+int hm_batch_clone(hm_context *ctx, const hm_batch *b, hm_batch **out) {
+    if (!ctx || !b || !out) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    hm_batch *c = new_batch(ctx, b->n, b->L, b->degb.data());
+    if (!c) return HM_ERR_INVALID_ARGUMENT;
+    int rc = alloc_batch(ctx, c);
+    if (rc != HM_OK) {
+        delete c;
+        return rc;
+    }
+    if (b->n) CK(cudaMemcpyAsync(c->d, b->d, b->n * b->value_words * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    *out = c;
+    return HM_OK;
+}
+
+void *hm_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void hm_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---- encrypt / decrypt ------------------------------------------------------------------------
+int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
+                      hm_batch **out) {
+    if (!ctx || !out || ((!d_values || !d_masks) && n)) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_pk) return HM_ERR_PUBLIC_KEY_UNSET; // context.rs:463-471
+    if (L == 0 || L % 8 != 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    std::vector<uint64_t> degb(L, ctx->fresh_deg);
+    hm_batch *b = new_batch(ctx, n, L, degb.data());
+    if (!b) return HM_ERR_INVALID_ARGUMENT;
+    int rc = alloc_batch(ctx, b);
+    if (rc != HM_OK) {
+        delete b;
+        return rc;
+    }
+    *out = b;
+    if (n == 0) return HM_OK;
+    hmk::EncParams p;
+    p.values = d_values;
+    p.masks = d_masks;
+    p.out = b->d;
+    p.table = ctx->d_enc_table;
+    p.units = (uint64_t)n * L;
+    p.wf = ctx->wf;
+    p.mask_bytes = (ctx->tau + 7u) / 8u;
+    p.wb = ctx->enc_wb;
+    p.groups = ctx->enc_groups;
+    p.table_words = ctx->enc_table_words;
+    p.table_in_smem = ctx->enc_table_in_smem ? 1 : 0;
+    const bool masks_aligned = ((uintptr_t)d_masks % 16) == 0;
+    const size_t table_bytes = ((size_t)p.table_words + 1) / 2 * 16;
+    int path = 0; // 0 generic, 1 config A tables, 2 config B tables
+    if (ctx->enc_table_in_smem && masks_aligned && p.wf == 5 && ctx->tau == 128 && p.wb == 8) path = 1;
+    if (ctx->enc_table_in_smem && masks_aligned && p.wf == 17 && ctx->tau == 256 && p.wb == 4 &&
+        table_bytes + 2 * (size_t)hmk::ENC_THREADS * 17 * 8 <= ctx->smem_optin)
+        path = 2;
+    if (path == 1) {
+        const size_t smem = table_bytes + 2 * (size_t)hmk::ENC_THREADS * 5 * 8;
+        auto kern = hmk::encrypt_tab_kernel<5, 4, 8>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = grid_for(ctx, p.units, hmk::ENC_THREADS, 1);
+        kern<<<grid, hmk::ENC_THREADS, smem, ctx->stream>>>(p);
+        LAUNCHED("encrypt_tab_kernel<5,4,8>");
+    } else if (path == 2) {
+        const size_t smem = table_bytes + 2 * (size_t)hmk::ENC_THREADS * 17 * 8;
+        auto kern = hmk::encrypt_tab_kernel<17, 8, 4>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = grid_for(ctx, p.units, hmk::ENC_THREADS, 1);
+        kern<<<grid, hmk::ENC_THREADS, smem, ctx->stream>>>(p);
+        LAUNCHED("encrypt_tab_kernel<17,8,4>");
+    } else {
+        const size_t smem = ctx->enc_table_in_smem ? (size_t)p.table_words * 8 : 0;
+        CK(cudaFuncSetAttribute(hmk::encrypt_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
+        const int grid = grid_for(ctx, p.units, 256, per_sm);
+        hmk::encrypt_generic_kernel<<<grid, 256, smem, ctx->stream>>>(p);
+        LAUNCHED("encrypt_generic_kernel");
+    }
+    return HM_OK;
+}
+
+int hm_encrypt(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, const uint8_t *masks, hm_batch **out) {
+    if (!ctx || !out || ((!values || !masks) && n)) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_pk) return HM_ERR_PUBLIC_KEY_UNSET;
+    if (L == 0 || L % 8 != 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    const size_t vbytes = n * (L / 8), mbytes = n * L * ((ctx->tau + 7u) / 8u);
+    uint8_t *dv = nullptr, *dm = nullptr;
+    CK(cudaMalloc(&dv, std::max<size_t>(vbytes, 16)));
+    cudaError_t e = cudaMalloc(&dm, std::max<size_t>(mbytes, 16));
+    if (e != cudaSuccess) {
+        cudaFree(dv);
+        return fail_cuda(ctx, e, "cudaMalloc(masks)");
+    }
+    int rc = HM_OK;
+    if (n) {
+        e = cudaMemcpyAsync(dv, values, vbytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dm, masks, mbytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = fail_cuda(ctx, e, "upload values/masks");
+    }
+    if (rc == HM_OK) rc = hm_encrypt_device(ctx, dv, n, L, dm, out);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(dv);
+    cudaFree(dm);
+    return rc;
+}
+
+int hm_decrypt_device(hm_context *ctx, const hm_batch *b, uint8_t *d_values_out) {
+    if (!ctx || !b || (!d_values_out && b->n)) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;       // context.rs:480-488
+    if (b->L % 8 != 0) return HM_ERR_INVALID_LENGTH;        // cipher.rs:218
+    USE_DEV(ctx);
+    if (b->n == 0) return HM_OK;
+    const uint64_t units = (uint64_t)b->n * b->L;
+    bool uniform = true;
+    for (uint32_t k = 1; k < b->L; ++k) uniform = uniform && (b->w[k] == b->w[0]);
+    const uint32_t w = b->w[0];
+    if (uniform && w <= 32 && ((uintptr_t)d_values_out % 4) == 0) {
+        int rc = ensure_decrypt_vector(ctx, (size_t)w * 64);
+        if (rc != HM_OK) return rc;
+        const size_t smem = ((size_t)((w + 1) & ~1u) + 2 * (size_t)hmk::DEC_THREADS * w) * 8;
+        CK(cudaFuncSetAttribute(hmk::decrypt_uniform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024)));
+        const int grid = grid_for(ctx, units, hmk::DEC_THREADS, per_sm);
+        hmk::decrypt_uniform_kernel<<<grid, hmk::DEC_THREADS, smem, ctx->stream>>>(b->d, ctx->d_v, d_values_out, units, w);
+        LAUNCHED("decrypt_uniform_kernel");
+    } else {
+        int rc = ensure_vv(ctx, b);
+        if (rc != HM_OK) return rc;
+        const uint64_t blocks = (units + 7) / 8;
+        if (blocks > 0x7fffffffull) return HM_ERR_UNSUPPORTED;
+        hmk::decrypt_slots_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(b->d, ctx->d_vv, d_values_out, units,
+                                                                            make_layout(b));
+        LAUNCHED("decrypt_slots_kernel");
+    }
+    return HM_OK;
+}
+
+int hm_decrypt(hm_context *ctx, const hm_batch *b, uint8_t *values_out) {
+    if (!ctx || !b || (!values_out && b->n)) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;
+    if (b->L % 8 != 0) return HM_ERR_INVALID_LENGTH;
+    USE_DEV(ctx);
+    const size_t bytes = b->n * (b->L / 8);
+    uint8_t *dout = nullptr;
+    CK(cudaMalloc(&dout, std::max<size_t>(bytes, 16)));
+    int rc = hm_decrypt_device(ctx, b, dout);
+    if (rc == HM_OK && bytes) {
+        cudaError_t e = cudaMemcpyAsync(values_out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = fail_cuda(ctx, e, "download plaintext");
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc == HM_OK && e != cudaSuccess) rc = fail_cuda(ctx, e, "decrypt sync");
+    cudaFree(dout);
+    return rc;
+}
+
+// ---- homomorphic operations -------------------------------------------------------------------
+int hm_op_min_d_over_delta(int op) { // reference src/impls/numbers.rs:27-50
+    switch (op) {
+        case HM_OP_AND: return 2;
+        case HM_OP_OR: return 2;
+        case HM_OP_XOR: return 1;
+        case HM_OP_NOT: return 1;
+        case HM_OP_ADD: return 21;
+        case HM_OP_MUL: return 64;
+        default: return HM_ERR_INVALID_ARGUMENT;
+    }
+}
+
+static int validate_operation(const hm_context *ctx, int op) { // context.rs:310-323
+    const int req = hm_op_min_d_over_delta(op);
+    if (req < 0) return req;
+    if ((uint32_t)ctx->d < (uint32_t)req * (uint32_t)ctx->delta) return HM_ERR_OPERATION_REQUIREMENT;
+    return HM_OK;
+}
+
+// Degree bounds of the result slots.  Shared by the planner and hm_result_slot_words.
+static int result_bounds(int op, uint32_t L, const uint64_t *da, const uint64_t *db, std::vector<uint64_t> &out) {
+    out.assign(L, 0);
+    switch (op) {
+        case HM_OP_XOR:
+            for (uint32_t k = 0; k < L; ++k) out[k] = std::max(da[k], db[k]);
+            return HM_OK;
+        case HM_OP_AND:
+        case HM_OP_OR:
+            for (uint32_t k = 0; k < L; ++k) out[k] = da[k] + db[k];
+            return HM_OK;
+        case HM_OP_ADD: { // common.rs:37-56 with carry_0 = 0
+            uint64_t dc = 0;
+            bool czero = true;
+            for (uint32_t k = 0; k < L; ++k) {
+                const uint64_t dpk = std::max(da[k], db[k]);
+                out[k] = czero ? dpk : std::max(dpk, dc);
+                if (k + 1 >= L) break;
+                const uint64_t dg = da[k] + db[k];
+                if (czero) {
+                    dc = dg; // carry_1 = a_0 * b_0
+                    czero = false;
+                } else {
+                    const uint64_t dcpp = dpk + dc;
+                    dc = dg + dcpp; // max(dcpp, dg + dcpp)
+                }
+            }
+            return HM_OK;
+        }
+        case HM_OP_MUL: { // common.rs:66-105
+            std::vector<uint64_t> carries;
+            std::vector<uint8_t> czero_flags;
+            size_t offset = 0;
+            for (uint32_t i = 0; i < L; ++i) {
+                const size_t cur = (size_t)i * (i + 1) / 2;
+                uint64_t dr = 0;
+                bool rz = true;
+                for (uint32_t j = 0; j <= i; ++j) {
+                    const uint64_t dpp = da[j] + db[i - j];
+                    if (i + 1 < L) {
+                        carries.push_back(rz ? 0 : dpp + dr);
+                        czero_flags.push_back(rz ? 1 : 0);
+                    }
+                    dr = rz ? dpp : std::max(dr, dpp);
+                    rz = false;
+                }
+                for (size_t j = 0; j < cur; ++j) {
+                    const uint64_t dcj = carries[offset + j];
+                    const bool cz = czero_flags[offset + j];
+                    if (i + 1 < L) {
+                        carries.push_back(cz ? 0 : dr + dcj);
+                        czero_flags.push_back(cz ? 1 : 0);
+                    }
+                    if (!cz) dr = std::max(dr, dcj);
+                }
+                offset += cur;
+                out[i] = dr;
+                if (dr > ((uint64_t)1 << 31)) return HM_ERR_UNSUPPORTED; // infeasible growth
+            }
+            return HM_OK;
+        }
+        default: return HM_ERR_INVALID_ARGUMENT;
+    }
+}
+
+int hm_result_slot_words(const hm_context *ctx, int op, uint32_t L, const uint32_t *a_words, const uint32_t *b_words,
+                         uint32_t *out_words) {
+    if (!ctx || !a_words || !b_words || !out_words || L == 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
+    std::vector<uint64_t> da(L), db(L), o;
+    for (uint32_t k = 0; k < L; ++k) {
+        // a width of exactly fresh size is taken as a fresh ciphertext (degree <= fresh_deg)
+        da[k] = (ctx->has_pk && a_words[k] == ctx->wf) ? ctx->fresh_deg : (uint64_t)a_words[k] * 64 - 1;
+        db[k] = (ctx->has_pk && b_words[k] == ctx->wf) ? ctx->fresh_deg : (uint64_t)b_words[k] * 64 - 1;
+    }
+    int rc = result_bounds(op, L, da.data(), db.data(), o);
+    if (rc != HM_OK) return rc;
+    for (uint32_t k = 0; k < L; ++k) out_words[k] = (uint32_t)(o[k] / 64 + 1);
+    return HM_OK;
+}
+
+// generic ripple-carry adder from views (any parameters / any input widths), reference order
+static int add_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
+    const uint32_t L = a->L;
+    const size_t n = a->n;
+    // arena per value: p, carry(2 buffers), cpp, cpp1, g, t — all at the final (largest) width
+    uint64_t maxdeg = 0;
+    for (uint32_t k = 0; k < L; ++k) maxdeg = std::max(maxdeg, o->degb[k]);
+    uint64_t dgmax = 0;
+    for (uint32_t k = 0; k < L; ++k) dgmax = std::max(dgmax, a->degb[k] + b->degb[k]);
+    const uint32_t wmax = (uint32_t)((maxdeg + dgmax) / 64 + 2);
+    const uint32_t NBUF = 7;
+    uint64_t *arena = nullptr;
+    const size_t arena_words = (size_t)NBUF * wmax;
+    CK(cudaMalloc(&arena, std::max<size_t>(n * arena_words * 8, 16)));
+    CK(cudaMemsetAsync(arena, 0, n * arena_words * 8, ctx->stream));
+    auto buf = [&](uint32_t i, uint64_t degb) {
+        View v;
+        v.base = arena;
+        v.stride = arena_words;
+        v.off = i * wmax;
+        v.w = (uint32_t)(degb / 64 + 1);
+        return v;
+    };
+    int rc = HM_OK;
+    uint64_t dc = 0;
+    bool czero = true;
+    uint32_t cur = 1; // carry buffers are 1 and 2
+    for (uint32_t k = 0; k < L && rc == HM_OK; ++k) {
+        const uint64_t dpk = std::max(a->degb[k], b->degb[k]);
+        View p = buf(0, dpk);
+        rc = launch_xor_views(ctx, p, slot_view(a, k), slot_view(b, k), n); // cb1.xor(cb2)
+        if (rc != HM_OK) break;
+        View sk = slot_view(o, k);
+        rc = launch_xor_views(ctx, sk, p, czero ? null_view() : buf(cur, dc), n); // .xor(&carry)
+        if (rc != HM_OK || k + 1 >= L) break;
+        const uint64_t dg = a->degb[k] + b->degb[k];
+        View g = buf(5, dg);
+        std::vector<MulOp> ops(1);
+        ops[0] = MulOp{slot_view(a, k), slot_view(b, k), g}; // cb1.and(cb2)
+        rc = launch_mul_ops(ctx, ops, n);
+        if (rc != HM_OK) break;
+        if (czero) { // c_p1_p2 = p * 0 = 0, carry = 0 + g * (0 + 1) = g
+            rc = launch_xor_views(ctx, buf(cur, dg), g, null_view(), n);
+            dc = dg;
+            czero = false;
+            continue;
+        }
+        const uint64_t dcpp = dpk + dc;
+        View cpp = buf(3, dcpp);
+        ops[0] = MulOp{p, buf(cur, dc), cpp}; // c_p1_p2 = p.and(carry)
+        rc = launch_mul_ops(ctx, ops, n);
+        if (rc != HM_OK) break;
+        View cpp1 = buf(4, dcpp);
+        rc = launch_xor_views(ctx, cpp1, cpp, null_view(), n); // copy, then + 1
+        if (rc != HM_OK) break;
+        {
+            Layout one;
+            one.L = 1;
+            one.value_words = (uint32_t)arena_words;
+            one.off[0] = cpp1.off;
+            one.off[1] = cpp1.off + cpp1.w;
+            const int grid = grid_for(ctx, n, 256, 16);
+            hmk::not_kernel<<<grid, 256, 0, ctx->stream>>>(arena, one, n); // c_p1_p2.xor(&one_bit)
+            rc = post_launch(ctx, "not_kernel");
+            if (rc != HM_OK) break;
+        }
+        const uint64_t dt = dg + dcpp;
+        View t = buf(6, dt);
+        ops[0] = MulOp{g, cpp1, t};
+        rc = launch_mul_ops(ctx, ops, n);
+        if (rc != HM_OK) break;
+        const uint32_t nxt = 3 - cur;
+        rc = launch_xor_views(ctx, buf(nxt, dt), cpp, t, n); // carry = c_p1_p2.xor(...)
+        cur = nxt;
+        dc = dt;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(arena);
+    return rc;
+}
+
+// generic unsigned multiplier circuit, reference common.rs:66-105
+static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
+    const uint32_t L = a->L;
+    const size_t n = a->n;
+    struct Obj {
+        uint32_t off, w_alloc;
+        uint64_t degb;
+        bool zero;
+    };
+    // plan: pp[j][k] for j+k < L, carries in push order; results live in the output batch
+    std::vector<std::vector<Obj>> pp(L, std::vector<Obj>(L));
+    uint64_t cursor = 0;
+    auto alloc = [&](uint64_t degb) {
+        Obj ob;
+        ob.off = (uint32_t)cursor;
+        ob.w_alloc = (uint32_t)(degb / 64 + 1);
+        ob.degb = degb;
+        ob.zero = false;
+        cursor += ob.w_alloc;
+        return ob;
+    };
+    for (uint32_t j = 0; j < L; ++j)
+        for (uint32_t k = 0; j + k < L; ++k) pp[j][k] = alloc(a->degb[j] + b->degb[k]);
+    // dry run for carry shapes
+    struct Step {
+        int kind; // 0 mul(o, x, y)   1 xor(res_i ^= x)
+        Obj o, x, y;
+        int res_i;
+        bool x_is_res, y_is_res;
+    };
+    std::vector<Obj> carries;
+    std::vector<Step> steps;
+    std::vector<uint64_t> dres(L, 0);
+    std::vector<bool> rzero(L, true);
+    size_t offset = 0;
+    for (uint32_t i = 0; i < L; ++i) {
+        const size_t curlen = (size_t)i * (i + 1) / 2;
+        auto res_obj = [&](uint32_t idx) {
+            Obj r;
+            r.off = o->off[idx];
+            r.w_alloc = o->w[idx];
+            r.degb = dres[idx];
+            r.zero = rzero[idx];
+            return r;
+        };
+        for (uint32_t j = 0; j <= i; ++j) {
+            const Obj &ppo = pp[j][i - j];
+            if (i + 1 < L) {
+                Obj c;
+                if (rzero[i]) {
+                    c = Obj{0, 0, 0, true};
+                } else {
+                    c = alloc(ppo.degb + dres[i]);
+                    steps.push_back(Step{0, c, ppo, res_obj(i), (int)i, false, true});
+                }
+                carries.push_back(c);
+            }
+            steps.push_back(Step{1, Obj{}, ppo, Obj{}, (int)i, false, false});
+            dres[i] = rzero[i] ? ppo.degb : std::max(dres[i], ppo.degb);
+            rzero[i] = false;
+        }
+        for (size_t j = 0; j < curlen; ++j) {
+            const Obj cj = carries[offset + j];
+            if (i + 1 < L) {
+                Obj c;
+                if (cj.zero) {
+                    c = Obj{0, 0, 0, true};
+                } else {
+                    c = alloc(dres[i] + cj.degb);
+                    steps.push_back(Step{0, c, res_obj(i), cj, (int)i, true, false});
+                }
+                carries.push_back(c);
+            }
+            if (!cj.zero) {
+                steps.push_back(Step{1, Obj{}, cj, Obj{}, (int)i, false, false});
+                dres[i] = std::max(dres[i], cj.degb);
+            }
+        }
+        offset += curlen;
+    }
+    const size_t arena_words = cursor;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if ((double)n * arena_words * 8.0 > 0.9 * (double)free_b) return HM_ERR_UNSUPPORTED;
+    uint64_t *arena = nullptr;
+    CK(cudaMalloc(&arena, std::max<size_t>(n * arena_words * 8, 16)));
+    CK(cudaMemsetAsync(o->d, 0, n * o->value_words * 8, ctx->stream));
+    auto aview = [&](const Obj &ob) {
+        View v;
+        v.base = arena;
+        v.stride = arena_words;
+        v.off = ob.off;
+        v.w = (uint32_t)(ob.degb / 64 + 1);
+        return v;
+    };
+    auto rview = [&](const Obj &ob) {
+        View v;
+        v.base = o->d;
+        v.stride = o->value_words;
+        v.off = ob.off;
+        v.w = (uint32_t)std::min<uint64_t>(ob.w_alloc, ob.degb / 64 + 1);
+        return v;
+    };
+    int rc = HM_OK;
+    { // all partial products in one launch (independent)
+        std::vector<MulOp> ops;
+        for (uint32_t j = 0; j < L; ++j)
+            for (uint32_t k = 0; j + k < L; ++k) ops.push_back(MulOp{slot_view(a, j), slot_view(b, k), aview(pp[j][k])});
+        rc = launch_mul_ops(ctx, ops, n);
+    }
+    std::vector<MulOp> one(1);
+    for (size_t s = 0; s < steps.size() && rc == HM_OK; ++s) {
+        const Step &st = steps[s];
+        if (st.kind == 0) {
+            one[0] = MulOp{st.x_is_res ? rview(st.x) : aview(st.x), st.y_is_res ? rview(st.y) : aview(st.y), aview(st.o)};
+            rc = launch_mul_ops(ctx, one, n);
+        } else {
+            View r;
+            r.base = o->d;
+            r.stride = o->value_words;
+            r.off = o->off[st.res_i];
+            r.w = o->w[st.res_i];
+            View x = aview(st.x);
+            // r ^= x over x's width only (words above are untouched)
+            View rr = r;
+            rr.w = std::min(r.w, x.w);
+            rc = launch_xor_views(ctx, rr, rr, x, n);
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(arena);
+    return rc;
+}
+
+static bool adder_fast_path_ok(const hm_context *ctx, const hm_batch *a, const hm_batch *b, size_t *smem_per_warp) {
+    if (!ctx->has_pk) return false;
+    const uint64_t D = ctx->fresh_deg;
+    if (D != 256) return false; // tuned instantiation: D = 32*8 (config A family)
+    for (uint32_t k = 0; k < a->L; ++k)
+        if (a->degb[k] != D || b->degb[k] != D) return false;
+    if (a->L < 2) return false;
+    const size_t words = hmk::AdderCfg<8>::warp_words(a->L);
+    *smem_per_warp = words * 4;
+    return words * 4 <= ctx->smem_optin;
+}
+
+// runs `op` into the already allocated result batch o (layout = result_bounds of the operands)
+static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch *o, bool force_generic) {
+    const size_t n = a->n;
+    if (n == 0) return HM_OK;
+    int rc = HM_OK;
+    switch (op) {
+        case HM_OP_XOR: rc = xor_batches(ctx, a, b, o); break;
+        case HM_OP_AND:
+        case HM_OP_OR: {
+            std::vector<MulOp> ops;
+            for (uint32_t k = 0; k < a->L; ++k) ops.push_back(MulOp{slot_view(a, k), slot_view(b, k), slot_view(o, k)});
+            rc = launch_mul_ops(ctx, ops, n);
+            if (rc == HM_OK && op == HM_OP_OR) { // a + b + a*b, cipher.rs:76-83
+                for (uint32_t k = 0; k < a->L && rc == HM_OK; ++k) {
+                    View ok = slot_view(o, k);
+                    rc = launch_xor_views(ctx, ok, ok, slot_view(a, k), n);
+                    if (rc == HM_OK) rc = launch_xor_views(ctx, ok, ok, slot_view(b, k), n);
+                }
+            }
+            break;
+        }
+        case HM_OP_ADD: {
+            size_t per_warp = 0;
+            if (!force_generic && adder_fast_path_ok(ctx, a, b, &per_warp)) {
+                int warps = (int)std::min<size_t>(4, ctx->smem_optin / per_warp);
+                if (warps < 1) warps = 1;
+                const size_t smem = per_warp * warps;
+                auto kern = hmk::adder_fused_kernel<8>;
+                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const unsigned grid = (unsigned)((n + warps - 1) / warps);
+                kern<<<grid, warps * 32, smem, ctx->stream>>>(a->d, b->d, o->d, n, a->L, make_layout(o));
+                rc = post_launch(ctx, "adder_fused_kernel");
+            } else {
+                rc = add_generic(ctx, a, b, o);
+            }
+            break;
+        }
+        case HM_OP_MUL: rc = mul_generic(ctx, a, b, o); break;
+        default: rc = HM_ERR_INVALID_ARGUMENT;
+    }
+    return rc;
+}
+
+static int apply2_impl(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch **out,
+                       bool force_generic = false) {
+    if (!ctx || !a || !b || !out) return HM_ERR_INVALID_ARGUMENT;
+    if (a->n != b->n || a->L != b->L) return HM_ERR_INVALID_ARGUMENT;
+    if (op == HM_OP_NOT) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    std::vector<uint64_t> bounds;
+    int rc = result_bounds(op, a->L, a->degb.data(), b->degb.data(), bounds);
+    if (rc != HM_OK) return rc;
+    hm_batch *o = new_batch(ctx, a->n, a->L, bounds.data());
+    if (!o) return HM_ERR_INVALID_ARGUMENT;
+    rc = alloc_batch(ctx, o);
+    if (rc != HM_OK) {
+        delete o;
+        return rc;
+    }
+    rc = apply2_exec(ctx, op, a, b, o, force_generic);
+    if (rc != HM_OK) {
+        hm_batch_free(ctx, o);
+        return rc;
+    }
+    *out = o;
+    return HM_OK;
+}
+
+int hm_apply2_unchecked(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch **out) {
+    return apply2_impl(ctx, op, a, b, out);
+}
+
+int hm_apply2_into(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch *out) {
+    if (!ctx || !a || !b || !out) return HM_ERR_INVALID_ARGUMENT;
+    int rc = validate_operation(ctx, op);
+    if (rc != HM_OK) return rc;
+    if (a->n != b->n || a->L != b->L || out->n != a->n || out->L != a->L || op == HM_OP_NOT) return HM_ERR_INVALID_ARGUMENT;
+    std::vector<uint64_t> bounds;
+    rc = result_bounds(op, a->L, a->degb.data(), b->degb.data(), bounds);
+    if (rc != HM_OK) return rc;
+    for (uint32_t k = 0; k < a->L; ++k)
+        if (out->w[k] != (uint32_t)(bounds[k] / 64 + 1)) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    out->degb = bounds;
+    return apply2_exec(ctx, op, a, b, out, false);
+}
+
+int hm_apply2(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch **out) {
+    if (!ctx) return HM_ERR_INVALID_ARGUMENT;
+    int rc = validate_operation(ctx, op);
+    if (rc != HM_OK) return rc;
+    return apply2_impl(ctx, op, a, b, out);
+}
+
+// forces the generic (view based, reference order) circuit even when the fused kernel applies; used to
+// cross-check the fused adder on the GPU.
+int hm_apply2_generic(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch **out) {
+    return apply2_impl(ctx, op, a, b, out, true);
+}
+
+int hm_apply1(hm_context *ctx, int op, hm_batch *a) {
+    if (!ctx || !a) return HM_ERR_INVALID_ARGUMENT;
+    if (op != HM_OP_NOT) return HM_ERR_INVALID_ARGUMENT;
+    int rc = validate_operation(ctx, op);
+    if (rc != HM_OK) return rc;
+    USE_DEV(ctx);
+    if (a->n == 0) return HM_OK;
+    const int grid = grid_for(ctx, (uint64_t)a->n * a->L, 256, 16);
+    hmk::not_kernel<<<grid, 256, 0, ctx->stream>>>(a->d, make_layout(a), a->n);
+    LAUNCHED("not_kernel");
+    return HM_OK;
+}
+
+int hm_apply2_host(hm_context *ctx, int op, size_t n, uint32_t L, const uint32_t *a_words, const uint64_t *a_host,
+                   const uint32_t *b_words, const uint64_t *b_host, uint64_t *out_host) {
+    if (!ctx || !a_words || !b_words || (!a_host && n) || (!b_host && n) || (!out_host && n)) return HM_ERR_INVALID_ARGUMENT;
+    int rc = validate_operation(ctx, op);
+    if (rc != HM_OK) return rc;
+    if (L == 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    std::vector<uint64_t> da(L), db(L);
+    size_t vwa = 0, vwb = 0;
+    for (uint32_t k = 0; k < L; ++k) {
+        if (!a_words[k] || !b_words[k]) return HM_ERR_INVALID_ARGUMENT;
+        da[k] = (ctx->has_pk && a_words[k] == ctx->wf) ? ctx->fresh_deg : (uint64_t)a_words[k] * 64 - 1;
+        db[k] = (ctx->has_pk && b_words[k] == ctx->wf) ? ctx->fresh_deg : (uint64_t)b_words[k] * 64 - 1;
+        vwa += a_words[k];
+        vwb += b_words[k];
+    }
+    std::vector<uint64_t> bo;
+    rc = result_bounds(op, L, da.data(), db.data(), bo);
+    if (rc != HM_OK) return rc;
+    size_t vwo = 0;
+    for (uint32_t k = 0; k < L; ++k) vwo += bo[k] / 64 + 1;
+    // chunked pipeline on three streams: upload of chunk c+1 and download of chunk c-1 overlap the
+    // kernels of chunk c.  Two stages of device buffers are allocated once and reused.
+    const size_t per_value_bytes = (vwa + vwb + vwo) * 8;
+    size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)384 << 20) / std::max<size_t>(per_value_bytes, 1)));
+    if (chunk > 1024) chunk &= ~(size_t)1023;
+    cudaStream_t user = ctx->stream;
+    cudaStream_t s_up = nullptr, s_down = nullptr;
+    CK(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking));
+    struct Stage {
+        hm_batch *a = nullptr, *b = nullptr, *o = nullptr;
+        cudaEvent_t up = nullptr, done = nullptr, down = nullptr;
+        bool used = false;
+    } st[2];
+    const int nstages = (n > chunk) ? 2 : 1;
+    for (int i = 0; i < nstages && rc == HM_OK; ++i) {
+        Stage &s = st[i];
+        cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.down, cudaEventDisableTiming);
+        s.a = new_batch(ctx, chunk, L, da.data());
+        s.b = new_batch(ctx, chunk, L, db.data());
+        s.o = new_batch(ctx, chunk, L, bo.data());
+        if (!s.a || !s.b || !s.o) rc = HM_ERR_INVALID_ARGUMENT;
+        if (rc == HM_OK) rc = alloc_batch(ctx, s.a);
+        if (rc == HM_OK) rc = alloc_batch(ctx, s.b);
+        if (rc == HM_OK) rc = alloc_batch(ctx, s.o);
+    }
+    size_t idx = 0;
+    for (size_t first = 0; first < n && rc == HM_OK; first += chunk, ++idx) {
+        Stage &s = st[idx % nstages];
+        const size_t cnt = std::min(chunk, n - first);
+        if (s.used) {
+            cudaStreamWaitEvent(s_up, s.done, 0); // inputs of this stage were consumed
+            cudaStreamWaitEvent(user, s.down, 0); // its previous result has left the device
+        }
+        s.a->n = s.b->n = s.o->n = cnt;
+        cudaMemcpyAsync(s.a->d, a_host + first * vwa, cnt * vwa * 8, cudaMemcpyHostToDevice, s_up);
+        cudaMemcpyAsync(s.b->d, b_host + first * vwb, cnt * vwb * 8, cudaMemcpyHostToDevice, s_up);
+        cudaEventRecord(s.up, s_up);
+        cudaStreamWaitEvent(user, s.up, 0);
+        rc = apply2_exec(ctx, op, s.a, s.b, s.o, false);
+        if (rc != HM_OK) break;
+        cudaEventRecord(s.done, user);
+        cudaStreamWaitEvent(s_down, s.done, 0);
+        cudaMemcpyAsync(out_host + first * vwo, s.o->d, cnt * vwo * 8, cudaMemcpyDeviceToHost, s_down);
+        cudaEventRecord(s.down, s_down);
+        s.used = true;
+    }
+    cudaStreamSynchronize(s_up);
+    cudaStreamSynchronize(user);
+    cudaError_t e = cudaStreamSynchronize(s_down);
+    for (int i = 0; i < nstages; ++i) {
+        Stage &s = st[i];
+        if (s.a) hm_batch_free(ctx, s.a);
+        if (s.b) hm_batch_free(ctx, s.b);
+        if (s.o) hm_batch_free(ctx, s.o);
+        if (s.up) cudaEventDestroy(s.up);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.down) cudaEventDestroy(s.down);
+    }
+    cudaStreamDestroy(s_up);
+    cudaStreamDestroy(s_down);
+    if (rc == HM_OK && e != cudaSuccess) rc = fail_cuda(ctx, e, "apply2_host");
+    return rc;
+}
+
+// ---- raw polynomial batches ----------------------------------------------------------------------
+int hm_poly_add(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out) {
+    return apply2_impl(ctx, HM_OP_XOR, a, b, out);
+}
+int hm_poly_mul(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out) {
+    return apply2_impl(ctx, HM_OP_AND, a, b, out);
+}
+
+int hm_poly_rem(hm_context *ctx, const hm_batch *a, hm_batch **out) {
+    if (!ctx || !a || !out) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;
+    USE_DEV(ctx);
+    std::vector<uint64_t> bounds(a->L, ctx->ds - 1);
+    hm_batch *o = new_batch(ctx, a->n, a->L, bounds.data());
+    if (!o) return HM_ERR_INVALID_ARGUMENT;
+    int rc = alloc_batch(ctx, o);
+    for (uint32_t k = 0; k < a->L && rc == HM_OK; ++k) rc = launch_rem(ctx, slot_view(a, k), slot_view(o, k), a->n);
+    if (rc != HM_OK) {
+        hm_batch_free(ctx, o);
+        return rc;
+    }
+    *out = o;
+    return HM_OK;
+}
+
+int hm_poly_mulrem(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out) {
+    if (!ctx || !a || !b || !out) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;
+    if (a->n != b->n || a->L != b->L) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    // fused fast path: both operands fresh-shaped with D = 256, d = 128 (config A)
+    bool fresh = ctx->has_pk && ctx->fresh_deg == 256 && ctx->ds == 128 && same_layout(a, b);
+    for (uint32_t k = 0; k < a->L && fresh; ++k) fresh = a->degb[k] == 256 && b->degb[k] == 256;
+    if (fresh) {
+        std::vector<uint64_t> bounds(a->L, ctx->ds - 1);
+        hm_batch *o = new_batch(ctx, a->n, a->L, bounds.data());
+        if (!o) return HM_ERR_INVALID_ARGUMENT;
+        int rc = alloc_batch(ctx, o);
+        if (rc != HM_OK) {
+            delete o;
+            return rc;
+        }
+        const uint64_t pairs = (uint64_t)a->n * a->L;
+        if (pairs) {
+            constexpr int WD = 8, WS = 4;
+            const size_t smem = (size_t)4 * 256 * WS * 4 + (size_t)2 * 2 * hmk::MR_THREADS * (WD / 2 + 1) * 8;
+            auto kern = hmk::mulrem_fresh_kernel<WD, WS>;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = grid_for(ctx, pairs, hmk::MR_THREADS, 6);
+            kern<<<grid, hmk::MR_THREADS, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
+            rc = post_launch(ctx, "mulrem_fresh_kernel");
+            if (rc != HM_OK) {
+                hm_batch_free(ctx, o);
+                return rc;
+            }
+        }
+        *out = o;
+        return HM_OK;
+    }
+    hm_batch *prod = nullptr;
+    int rc = hm_poly_mul(ctx, a, b, &prod);
+    if (rc != HM_OK) return rc;
+    rc = hm_poly_rem(ctx, prod, out);
+    hm_batch_free(ctx, prod);
+    return rc;
+}
+
+// ---- measured integer-logic peak ------------------------------------------------------------------
+int hm_measure_alu_peak(hm_context *ctx, double *lop3_lane_ops_per_s, double *sm_clock_mhz) {
+    if (!ctx || !lop3_lane_ops_per_s) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    uint32_t *sink = nullptr;
+    unsigned long long *clk = nullptr;
+    CK(cudaMalloc(&sink, (size_t)blocks * threads * 4));
+    CK(cudaMalloc(&clk, (size_t)blocks * 8));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 8192;
+    hmk::lop3_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(sink, clk, iters, 0x9e3779b9u);
+    double best = 0, mhz = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, ctx->stream);
+        hmk::lop3_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(sink, clk, iters, 0x9e3779b9u + rep);
+        cudaEventRecord(e1, ctx->stream);
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        std::vector<unsigned long long> h(blocks);
+        CK(cudaMemcpy(h.data(), clk, (size_t)blocks * 8, cudaMemcpyDeviceToHost));
+        double avg = 0;
+        for (int i = 0; i < blocks; ++i) avg += (double)h[i];
+        avg /= blocks;
+        const double ops = (double)blocks * threads * iters * hmk::PEAK_ILP;
+        const double rate = ops / (ms * 1e-3);
+        if (rate > best) {
+            best = rate;
+            mhz = avg / (ms * 1e3);
+        }
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(clk);
+    *lop3_lane_ops_per_s = best;
+    if (sm_clock_mhz) *sm_clock_mhz = mhz;
+    return HM_OK;
+}
+
+// ---- host-side helpers ---------------------------------------------------------------------------
+uint32_t hm_fresh_slot_words(const hm_context *ctx) {
+    if (!ctx) return 0;
+    if (ctx->has_pk) return ctx->wf;
+    return (uint32_t)(((size_t)ctx->d + ctx->dp) / 64 + 1);
+}
+
+int hm_decrypt_vector(const hm_context *ctx, size_t nbits, uint64_t *v_out) {
+    if (!ctx || !v_out) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;
+    gf2::words v = gf2::decrypt_vector(ctx->S, ctx->ds, nbits);
+    for (size_t i = 0; i < (nbits + 63) / 64; ++i) v_out[i] = v[i];
+    if (nbits % 64) v_out[nbits / 64] &= (((uint64_t)1 << (nbits % 64)) - 1);
+    return HM_OK;
+}
+
+size_t hm_poly_degree(const uint64_t *words, size_t n_words) {
+    if (!words || n_words == 0) return 0;
+    return gf2::degree(words, n_words);
+}
+
+} // extern "C"

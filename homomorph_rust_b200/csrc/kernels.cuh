@@ -1,0 +1,885 @@
+// kernels.cuh — hand-written sm_100a kernels of the batched GF(2)[X] ciphertext engine.
+//
+// Data model: a batch is n values x L bit-ciphertext slots; slot k of every
+// value has the same fixed width in 64-bit words; value v occupies words
+// [v*value_words, (v+1)*value_words) of one HBM allocation ("padded layout", value-major).
+// Words are the reference's coefficient words: X^i is bit i%64 of word i/64
+// (reference src/polynomial.rs:144,172).  Kernels work on the same memory as 32-bit words
+// (little endian), since the SM integer datapath is 32 bits wide.
+//
+// Kernel -> reference map
+//   encrypt_*            CipheredBit::cipher        src/cipher.rs:99-115 (+ loop :180-185)
+//   decrypt_*            CipheredBit::decipher      src/cipher.rs:119-122 (+ packing :227-237)
+//   xor_* / not_kernel   Polynomial::add, gate_xor/not   src/polynomial.rs:190-243, common.rs:21-35
+//   mul_views_kernel     Polynomial::mul            src/polynomial.rs:252-310
+//   rem_*                Polynomial::rem            src/polynomial.rs:316-365
+//   mulrem_fresh_kernel  mul followed by rem (the BASELINE "mul+rem" unit)
+//   adder_fused_kernel   add_internal               src/impls/numbers/common.rs:37-56
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hmk {
+
+constexpr int MAX_SLOTS = 128;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct Layout { // slot layout of a batch, in u64 words
+    uint32_t L;
+    uint32_t value_words;
+    uint32_t off[MAX_SLOTS + 1];
+};
+
+struct View { // one slot of every value of some buffer
+    uint64_t *base;
+    uint64_t stride; // u64 words between consecutive values
+    uint32_t off;    // u64 word offset of the slot inside a value
+    uint32_t w;      // slot width in u64 words
+};
+
+struct MulOp {
+    View a, b, o;
+};
+
+// ----------------------------------------------------------------------------------------
+// TMA (1-D bulk copy) + mbarrier helpers
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared, completion counted in bytes on `bar`.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk store (bulk async-group completion).
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------
+// K2  subset-XOR encryption                         reference src/cipher.rs:99-115
+//
+//   C = XOR_{i : mask bit i} T_i  XOR  x
+// The tau-bit subset mask is cut into windows of WB bits; for every window the XOR of every
+// subset of its WB public-key polynomials is tabulated once per key (Method of Four
+// Russians): table[g][e][0..WF).  A bit-ciphertext is then tau/WB row XORs.  The table
+// (160 KB at d=d'=128, tau=128, WB=8) lives in shared memory of persistent CTAs.
+// ----------------------------------------------------------------------------------------
+struct EncParams {
+    const uint8_t *values; // n * L/8 bytes
+    const uint8_t *masks;  // units * mask_bytes
+    uint64_t *out;         // units * wf words
+    const uint64_t *table; // groups * 2^wb * wf words (global copy)
+    uint64_t units;        // n * L bit-ciphertexts
+    uint32_t wf;           // u64 words per fresh slot
+    uint32_t mask_bytes;   // ceil(tau/8)
+    uint32_t wb;           // window bits (1,2,4,8)
+    uint32_t groups;       // ceil(tau/wb)
+    uint32_t table_words;  // groups << wb * wf
+    uint32_t table_in_smem;
+};
+
+constexpr int ENC_THREADS = 512;
+
+// Fast path: WF words per slot, MW 32-bit mask words (tau == 32*MW), window WB.
+template <int WF, int MW, int WB>
+__global__ void __launch_bounds__(ENC_THREADS, 1) encrypt_tab_kernel(EncParams p) {
+    extern __shared__ __align__(16) uint64_t smem64[];
+    uint64_t *tab = smem64;                              // table_words
+    uint64_t *stage = smem64 + ((p.table_words + 1) & ~1u); // 2 x ENC_THREADS*WF, 16-byte aligned
+    const int tid = threadIdx.x;
+    // table: global -> shared, 128-bit coalesced
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.table);
+        uint4 *dst = reinterpret_cast<uint4 *>(tab);
+        const uint32_t n16 = p.table_words / 2;
+        for (uint32_t i = tid; i < n16; i += ENC_THREADS) dst[i] = __ldg(src + i);
+        if ((p.table_words & 1) && tid == 0) tab[p.table_words - 1] = p.table[p.table_words - 1];
+    }
+    __syncthreads();
+    constexpr int GROUPS = MW * 32 / WB;
+    const uint64_t ntiles = (p.units + ENC_THREADS - 1) / ENC_THREADS;
+    uint32_t it = 0;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        uint64_t *st = stage + (size_t)(it & 1) * ENC_THREADS * WF;
+        // the bulk store issued two iterations ago from this buffer must have read it
+        if (tid == 0) tma_store_wait_read<1>();
+        __syncthreads();
+        const uint64_t u = t * ENC_THREADS + tid;
+        uint64_t acc[WF];
+#pragma unroll
+        for (int j = 0; j < WF; ++j) acc[j] = 0;
+        if (u < p.units) {
+            uint32_t mk[MW];
+            const uint4 *mp = reinterpret_cast<const uint4 *>(p.masks + u * (uint64_t)(MW * 4));
+#pragma unroll
+            for (int q = 0; q < MW / 4; ++q) {
+                uint4 m4 = __ldg(mp + q);
+                mk[4 * q + 0] = m4.x;
+                mk[4 * q + 1] = m4.y;
+                mk[4 * q + 2] = m4.z;
+                mk[4 * q + 3] = m4.w;
+            }
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g) {
+                const uint32_t e = (mk[(g * WB) / 32] >> ((g * WB) % 32)) & ((1u << WB) - 1u);
+                const uint64_t *row = tab + ((size_t)((g << WB) + e)) * WF;
+#pragma unroll
+                for (int j = 0; j < WF; ++j) acc[j] ^= row[j];
+            }
+            const uint32_t bit = (__ldg(p.values + (u >> 3)) >> (u & 7)) & 1u; // src/cipher.rs:180-185
+            acc[0] ^= bit;                                                      // add_bool_assign, polynomial.rs:238-243
+        }
+#pragma unroll
+        for (int j = 0; j < WF; ++j) st[(size_t)tid * WF + j] = acc[j];
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            const uint64_t first = t * ENC_THREADS;
+            const uint64_t cnt = (p.units - first < ENC_THREADS) ? (p.units - first) : ENC_THREADS;
+            const uint32_t bytes = (uint32_t)(cnt * WF * 8);
+            if ((bytes & 15u) == 0) {
+                tma_store_1d(p.out + first * WF, st, bytes);
+            } else { // ragged tail: plain stores by one thread (at most one tile per launch)
+                for (uint32_t i = 0; i < cnt * WF; ++i) p.out[first * WF + i] = st[i];
+            }
+            tma_store_commit();
+        }
+    }
+    if (tid == 0) tma_store_wait_all();
+}
+
+// Generic path: any tau / D / window, table read from shared memory if it fits, else from L2.
+__global__ void __launch_bounds__(256) encrypt_generic_kernel(EncParams p) {
+    extern __shared__ __align__(16) uint64_t smem64[];
+    const uint64_t *tab = p.table;
+    if (p.table_in_smem) {
+        for (uint32_t i = threadIdx.x; i < p.table_words; i += blockDim.x) smem64[i] = p.table[i];
+        __syncthreads();
+        tab = smem64;
+    }
+    const uint32_t emask = (1u << p.wb) - 1u;
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < p.units; u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t *mk = p.masks + u * p.mask_bytes;
+        const uint32_t bit = (p.values[u >> 3] >> (u & 7)) & 1u;
+        for (uint32_t j = 0; j < p.wf; ++j) {
+            uint64_t acc = (j == 0) ? bit : 0;
+            for (uint32_t g = 0; g < p.groups; ++g) {
+                const uint32_t bitpos = g * p.wb;
+                const uint32_t e = (mk[bitpos >> 3] >> (bitpos & 7)) & emask;
+                acc ^= tab[((size_t)((g << p.wb) + e)) * p.wf + j];
+            }
+            p.out[u * p.wf + j] = acc;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// K3  decryption = parity(popcount(C AND v)),  v_k = (X^k mod S)(0)
+//     identical to rem + evaluate(false)            reference src/cipher.rs:119-122
+// ----------------------------------------------------------------------------------------
+constexpr int DEC_THREADS = 256;
+
+// Uniform slot width w (fresh ciphertexts): tiles of 256 slots staged in shared memory by TMA,
+// double buffered; thread per slot; result bits packed by ballot (bit k of the value is slot k,
+// src/cipher.rs:227-237, so 32 consecutive slots are 4 consecutive output bytes).
+__global__ void __launch_bounds__(DEC_THREADS) decrypt_uniform_kernel(const uint64_t *__restrict__ ct,
+                                                                      const uint64_t *__restrict__ v,
+                                                                      uint8_t *__restrict__ out, uint64_t units,
+                                                                      uint32_t w) {
+    extern __shared__ __align__(16) uint64_t smem64[];
+    __shared__ __align__(8) uint64_t bars[2];
+    uint64_t *sv = smem64;                       // w words (padded to even)
+    uint64_t *tiles = smem64 + ((w + 1) & ~1u);  // 2 x 256*w
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t tile_words = DEC_THREADS * w;
+    for (uint32_t i = tid; i < w; i += DEC_THREADS) sv[i] = v[i];
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint64_t nfull = units / DEC_THREADS;
+    uint32_t it = 0;
+    if (tid == 0 && blockIdx.x < nfull) {
+        mbar_expect_tx(&bars[0], tile_words * 8);
+        tma_load_1d(tiles, ct + (uint64_t)blockIdx.x * tile_words, tile_words * 8, &bars[0]);
+    }
+    for (uint64_t t = blockIdx.x; t < nfull; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        const uint64_t tn = t + gridDim.x;
+        if (tid == 0 && tn < nfull) { // prefetch next tile into the other buffer (freed by the barrier below)
+            mbar_expect_tx(&bars[buf ^ 1], tile_words * 8);
+            tma_load_1d(tiles + (size_t)(buf ^ 1) * tile_words, ct + tn * tile_words, tile_words * 8, &bars[buf ^ 1]);
+        }
+        mbar_wait(&bars[buf], (it >> 1) & 1);
+        const uint64_t *c = tiles + (size_t)buf * tile_words + (size_t)tid * w;
+        uint64_t acc = 0;
+        for (uint32_t j = 0; j < w; ++j) acc ^= c[j] & sv[j];
+        const uint32_t bit = __popcll(acc) & 1u;
+        const uint32_t word = __ballot_sync(FULL, bit);
+        if (lane == 0) reinterpret_cast<uint32_t *>(out)[(t * DEC_THREADS + tid) >> 5] = word;
+        __syncthreads();
+    }
+    // ragged tail (< 256 slots): straight from global memory, handled by block 0
+    if (blockIdx.x == 0 && nfull * DEC_THREADS < units) {
+        const uint64_t u = nfull * DEC_THREADS + tid;
+        uint32_t bit = 0;
+        if (u < units) {
+            const uint64_t *c = ct + u * w;
+            uint64_t acc = 0;
+            for (uint32_t j = 0; j < w; ++j) acc ^= c[j] & sv[j];
+            bit = __popcll(acc) & 1u;
+        }
+        const uint32_t word = __ballot_sync(FULL, bit);
+        if ((lane & 7) == 0 && u < units) out[u >> 3] = (uint8_t)(word >> lane);
+    }
+}
+
+// Any slot layout: one warp per slot, lanes stride the slot's words (coalesced), shuffle parity.
+// vv is v laid out like one value: vv[off[k] + j] = v[j].
+__global__ void __launch_bounds__(256) decrypt_slots_kernel(const uint64_t *__restrict__ ct,
+                                                            const uint64_t *__restrict__ vv,
+                                                            uint8_t *__restrict__ out, uint64_t units, Layout lay) {
+    __shared__ uint32_t bits;
+    if (threadIdx.x == 0) bits = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t u = (uint64_t)blockIdx.x * 8 + warp;
+    if (u < units) {
+        const uint64_t val = u / lay.L;
+        const uint32_t k = (uint32_t)(u % lay.L);
+        const uint32_t o = lay.off[k], w = lay.off[k + 1] - o;
+        const uint64_t *c = ct + val * lay.value_words + o;
+        const uint64_t *vk = vv + o;
+        uint64_t acc = 0;
+        uint32_t j = lane;
+        for (; j + 96 < w; j += 128) {
+            const uint64_t c0 = __ldg(c + j), c1 = __ldg(c + j + 32), c2 = __ldg(c + j + 64), c3 = __ldg(c + j + 96);
+            acc ^= (c0 & __ldg(vk + j)) ^ (c1 & __ldg(vk + j + 32)) ^ (c2 & __ldg(vk + j + 64)) ^ (c3 & __ldg(vk + j + 96));
+        }
+        for (; j < w; j += 32) acc ^= __ldg(c + j) & __ldg(vk + j);
+        uint32_t par = __popcll(acc) & 1u;
+        par ^= __shfl_xor_sync(FULL, par, 16);
+        par ^= __shfl_xor_sync(FULL, par, 8);
+        par ^= __shfl_xor_sync(FULL, par, 4);
+        par ^= __shfl_xor_sync(FULL, par, 2);
+        par ^= __shfl_xor_sync(FULL, par, 1);
+        if (lane == 0 && par) atomicOr(&bits, 1u << warp);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && (uint64_t)blockIdx.x * 8 < units) out[blockIdx.x] = (uint8_t)bits;
+}
+
+// ----------------------------------------------------------------------------------------
+// K1  XOR / NOT                                     reference src/polynomial.rs:190-243
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) xor_flat_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b,
+                                                       uint4 *__restrict__ o, uint64_t n16) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 x = __ldg(a + i), y = __ldg(b + i);
+        o[i] = make_uint4(x.x ^ y.x, x.y ^ y.y, x.z ^ y.z, x.w ^ y.w);
+    }
+}
+__global__ void __launch_bounds__(256) xor_flat_tail_kernel(const uint64_t *a, const uint64_t *b, uint64_t *o,
+                                                            uint64_t from, uint64_t to) {
+    const uint64_t i = from + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < to) o[i] = a[i] ^ b[i];
+}
+// Different layouts: out slot k = a slot k XOR b slot k, each zero-extended to the output width.
+__global__ void __launch_bounds__(256) xor_layout_kernel(const uint64_t *__restrict__ a, Layout la,
+                                                         const uint64_t *__restrict__ b, Layout lb,
+                                                         uint64_t *__restrict__ o, Layout lo, uint64_t n) {
+    const uint64_t total = n * lo.value_words;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = i / lo.value_words;
+        const uint32_t p = (uint32_t)(i % lo.value_words);
+        uint32_t lo_k = 0, hi_k = lo.L; // slot k with off[k] <= p < off[k+1]
+        while (hi_k - lo_k > 1) {
+            const uint32_t mid = (lo_k + hi_k) >> 1;
+            if (lo.off[mid] <= p) lo_k = mid; else hi_k = mid;
+        }
+        const uint32_t k = lo_k, j = p - lo.off[k];
+        uint64_t x = 0;
+        if (j < la.off[k + 1] - la.off[k]) x ^= a[v * la.value_words + la.off[k] + j];
+        if (j < lb.off[k + 1] - lb.off[k]) x ^= b[v * lb.value_words + lb.off[k] + j];
+        o[i] = x;
+    }
+}
+// gate_not: a + 1, flips the constant term of every slot (common.rs:29-35).
+__global__ void __launch_bounds__(256) not_kernel(uint64_t *d, Layout lay, uint64_t n) {
+    const uint64_t total = n * lay.L;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = i / lay.L;
+        const uint32_t k = (uint32_t)(i % lay.L);
+        d[v * lay.value_words + lay.off[k]] ^= 1ull;
+    }
+}
+// o[v][0..o.w) = (zero-extended) a[v] XOR b[v];  b.base may be null (copy / widen).  In place allowed
+// when o aliases a or b slot-for-slot.
+__global__ void __launch_bounds__(256) xor_views_kernel(View o, View a, View b, uint64_t n) {
+    const uint64_t total = n * o.w;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = i / o.w;
+        const uint32_t j = (uint32_t)(i % o.w);
+        uint64_t x = 0;
+        if (j < a.w) x ^= a.base[v * a.stride + a.off + j];
+        if (b.base && j < b.w) x ^= b.base[v * b.stride + b.off + j];
+        o.base[v * o.stride + o.off + j] = x;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// K4  generic carry-less multiply, one warp per product     reference src/polynomial.rs:252-310
+//
+// Operands staged in shared memory; output words sliced over the lanes; the shorter operand is
+// scanned word by word and its set bits are warp-uniform, so zero bits cost nothing.
+// ----------------------------------------------------------------------------------------
+constexpr int MUL_WARPS = 4;
+
+__global__ void __launch_bounds__(MUL_WARPS * 32) mul_views_kernel(const MulOp *__restrict__ ops, uint64_t n,
+                                                                   uint32_t smem_words_per_warp) {
+    extern __shared__ __align__(16) uint32_t smem32[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t v = (uint64_t)blockIdx.x * MUL_WARPS + warp;
+    if (v >= n) return;
+    const MulOp op = ops[blockIdx.y];
+    const uint32_t *ga = reinterpret_cast<const uint32_t *>(op.a.base + v * op.a.stride + op.a.off);
+    const uint32_t *gb = reinterpret_cast<const uint32_t *>(op.b.base + v * op.b.stride + op.b.off);
+    uint32_t na = 2 * op.a.w, nb = 2 * op.b.w;
+    if (na > nb) { // scan the shorter operand
+        const uint32_t *tp = ga; ga = gb; gb = tp;
+        const uint32_t tn = na; na = nb; nb = tn;
+    }
+    uint32_t *sa = smem32 + (size_t)warp * smem_words_per_warp;
+    uint32_t *sb = sa + na;
+    for (uint32_t i = lane; i < na; i += 32) sa[i] = ga[i];
+    for (uint32_t i = lane; i < nb; i += 32) sb[i] = gb[i];
+    __syncwarp();
+    uint32_t *go = reinterpret_cast<uint32_t *>(op.o.base + v * op.o.stride + op.o.off);
+    const uint32_t no = 2 * op.o.w;
+    for (uint32_t r0 = 0; r0 < no; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        uint32_t acc = 0;
+        // a[j] * b[r-j] (low half) and a[j] * b[r-j-1] (high half); j such that some lane has 0 <= r-j <= nb
+        const uint32_t jlo = (r0 > nb) ? (r0 - nb) : 0;
+        const uint32_t jhi = (r0 + 31 < na - 1) ? (r0 + 31) : (na - 1);
+        for (uint32_t j = jlo; j <= jhi && j < na; ++j) {
+            uint32_t aw = sa[j];
+            if (aw == 0) continue; // warp-uniform
+            const int bi = (int)r - (int)j;
+            const uint32_t hi = (bi >= 0 && bi < (int)nb) ? sb[bi] : 0u;
+            const uint32_t lo = (bi >= 1 && bi - 1 < (int)nb) ? sb[bi - 1] : 0u;
+            while (aw) { // warp-uniform trip count
+                const int s = __ffs(aw) - 1;
+                aw &= aw - 1;
+                acc ^= __funnelshift_l(lo, hi, s);
+            }
+        }
+        if (r < no) go[r] = acc;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// register-resident schoolbook product of NA x NB 32-bit words (per-thread operands)
+// Horner over the bit index of a: r = r*X ^ sum_j (bit s of a[j]) * b * X^(32 j)
+// ----------------------------------------------------------------------------------------
+template <int NA, int NB>
+__device__ __forceinline__ void clmul_regs(const uint32_t (&a)[NA], const uint32_t (&b)[NB], uint32_t (&r)[NA + NB]) {
+#pragma unroll
+    for (int i = 0; i < NA + NB; ++i) r[i] = 0;
+    uint32_t at[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) at[j] = a[j];
+#pragma unroll 1
+    for (int s = 0; s < 32; ++s) {
+#pragma unroll
+        for (int i = NA + NB - 1; i > 0; --i) r[i] = __funnelshift_l(r[i - 1], r[i], 1);
+        r[0] <<= 1;
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const uint32_t m = (uint32_t)((int32_t)at[j] >> 31); // current top bit of a[j], as a mask
+            at[j] <<= 1;
+#pragma unroll
+            for (int k = 0; k < NB; ++k) r[j + k] ^= b[k] & m;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// K5  remainder by the secret key S                  reference src/polynomial.rs:316-365
+//
+// d % 32 == 0: word folding, T[b][x] = (x * X^(8b) * X^d) mod S (gf2host.hpp), i.e. a CRC with
+// four 256-entry tables; WS = d/32 words of state in registers.
+// ----------------------------------------------------------------------------------------
+template <int WS>
+__device__ __forceinline__ void fold_word(uint32_t (&dst)[WS], uint32_t t, const uint32_t *__restrict__ T) {
+    const uint32_t *r0 = T + (size_t)(0 * 256 + (t & 255u)) * WS;
+    const uint32_t *r1 = T + (size_t)(1 * 256 + ((t >> 8) & 255u)) * WS;
+    const uint32_t *r2 = T + (size_t)(2 * 256 + ((t >> 16) & 255u)) * WS;
+    const uint32_t *r3 = T + (size_t)(3 * 256 + (t >> 24)) * WS;
+    if constexpr (WS % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < WS / 4; ++q) {
+            const uint4 x0 = reinterpret_cast<const uint4 *>(r0)[q], x1 = reinterpret_cast<const uint4 *>(r1)[q];
+            const uint4 x2 = reinterpret_cast<const uint4 *>(r2)[q], x3 = reinterpret_cast<const uint4 *>(r3)[q];
+            dst[4 * q + 0] ^= x0.x ^ x1.x ^ x2.x ^ x3.x;
+            dst[4 * q + 1] ^= x0.y ^ x1.y ^ x2.y ^ x3.y;
+            dst[4 * q + 2] ^= x0.z ^ x1.z ^ x2.z ^ x3.z;
+            dst[4 * q + 3] ^= x0.w ^ x1.w ^ x2.w ^ x3.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < WS; ++q) dst[q] ^= r0[q] ^ r1[q] ^ r2[q] ^ r3[q];
+    }
+}
+
+template <int WS>
+__global__ void __launch_bounds__(128) rem_fold_kernel(View a, View o, uint64_t n, const uint32_t *__restrict__ Tg) {
+    extern __shared__ __align__(16) uint32_t smem32[];
+    for (uint32_t i = threadIdx.x; i < 4u * 256u * WS; i += blockDim.x) smem32[i] = Tg[i];
+    __syncthreads();
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(a.base + v * a.stride + a.off);
+    const int na = 2 * (int)a.w;
+    uint32_t r[WS];
+#pragma unroll
+    for (int q = 0; q < WS; ++q) r[q] = 0;
+    for (int i = na - 1; i >= 0; --i) { // r = (r * X^32 + word_i) mod S
+        const uint32_t t = r[WS - 1];
+#pragma unroll
+        for (int q = WS - 1; q > 0; --q) r[q] = r[q - 1];
+        r[0] = p[i];
+        if (t) fold_word<WS>(r, t, smem32);
+    }
+    uint32_t *out = reinterpret_cast<uint32_t *>(o.base + v * o.stride + o.off);
+#pragma unroll
+    for (int q = 0; q < WS; ++q) out[q] = r[q];
+    for (uint32_t q = WS; q < 2 * o.w; ++q) out[q] = 0;
+}
+
+// Any d >= 1: warp-cooperative long division in shared memory (slow; small/odd parameter sets only).
+__global__ void __launch_bounds__(MUL_WARPS * 32) rem_generic_kernel(View a, View o, uint64_t n,
+                                                                     const uint32_t *__restrict__ Sg, uint32_t d,
+                                                                     uint32_t smem_words_per_warp) {
+    extern __shared__ __align__(16) uint32_t smem32[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t v = (uint64_t)blockIdx.x * MUL_WARPS + warp;
+    if (v >= n) return;
+    uint32_t *sp = smem32 + (size_t)warp * smem_words_per_warp;
+    const uint32_t na = 2 * a.w, ns = d / 32 + 1;
+    const uint32_t *ga = reinterpret_cast<const uint32_t *>(a.base + v * a.stride + a.off);
+    for (uint32_t i = lane; i < na; i += 32) sp[i] = ga[i];
+    if (lane == 0) sp[na] = 0; // spill word for the shifted divisor
+    __syncwarp();
+    for (int pos = (int)na * 32 - 1; pos >= (int)d; --pos) {
+        const uint32_t wv = sp[pos >> 5];
+        if ((wv >> (pos & 31)) & 1u) { // warp-uniform
+            const uint32_t sh = (uint32_t)pos - d, ws = sh >> 5, bs = sh & 31;
+            for (uint32_t i = lane; i <= ns; i += 32) { // S << sh covers words ws .. ws+ns
+                const uint32_t hi = (i < ns) ? Sg[i] : 0u, lo = (i >= 1) ? Sg[i - 1] : 0u;
+                const uint32_t x = __funnelshift_l(lo, hi, bs);
+                if (x) sp[ws + i] ^= x;
+            }
+        }
+        __syncwarp();
+    }
+    uint32_t *out = reinterpret_cast<uint32_t *>(o.base + v * o.stride + o.off);
+    for (uint32_t q = lane; q < 2 * o.w; q += 32) out[q] = (q < na) ? sp[q] : 0u;
+}
+
+// ----------------------------------------------------------------------------------------
+// Fused (a*b) mod S for fresh ciphertext pairs, thread per pair       BASELINE "mul+rem"
+//   D = 32*WD (D % 64 == 0): operands are WD words + the X^D bit; d = 32*WS.
+//   Operand tiles are staged in shared memory by TMA (two buffers); the 2D+1-bit product stays
+//   in registers and is folded down to d bits with the tables above; only d bits are written.
+// ----------------------------------------------------------------------------------------
+constexpr int MR_THREADS = 128;
+
+template <int WD, int WS>
+__global__ void __launch_bounds__(MR_THREADS) mulrem_fresh_kernel(const uint64_t *__restrict__ A,
+                                                                  const uint64_t *__restrict__ B,
+                                                                  uint64_t *__restrict__ O, uint64_t n,
+                                                                  const uint32_t *__restrict__ Tg) {
+    constexpr int WF = WD / 2 + 1;   // u64 words per operand slot
+    constexpr int NP = 2 * WD + 1;   // product words (bit 2D lives in the last one)
+    extern __shared__ __align__(16) uint32_t smem32[];
+    __shared__ __align__(8) uint64_t bars[2];
+    uint32_t *T = smem32;                                               // 4*256*WS
+    uint64_t *tiles = reinterpret_cast<uint64_t *>(smem32 + 4 * 256 * WS); // [2 bufs][2 operands][MR_THREADS*WF]
+    const int tid = threadIdx.x;
+    for (uint32_t i = tid; i < 4u * 256u * WS; i += MR_THREADS) T[i] = Tg[i];
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    constexpr uint32_t TILE_WORDS = MR_THREADS * WF;
+    const uint64_t nfull = n / MR_THREADS;
+    const uint64_t ntiles = (n + MR_THREADS - 1) / MR_THREADS;
+    if (tid == 0 && blockIdx.x < nfull) {
+        mbar_expect_tx(&bars[0], 2 * TILE_WORDS * 8);
+        tma_load_1d(tiles, A + (uint64_t)blockIdx.x * TILE_WORDS, TILE_WORDS * 8, &bars[0]);
+        tma_load_1d(tiles + TILE_WORDS, B + (uint64_t)blockIdx.x * TILE_WORDS, TILE_WORDS * 8, &bars[0]);
+    }
+    uint32_t it = 0;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        const uint64_t tn = t + gridDim.x;
+        if (tid == 0 && tn < nfull) {
+            uint64_t *dst = tiles + (size_t)(buf ^ 1) * 2 * TILE_WORDS;
+            mbar_expect_tx(&bars[buf ^ 1], 2 * TILE_WORDS * 8);
+            tma_load_1d(dst, A + tn * TILE_WORDS, TILE_WORDS * 8, &bars[buf ^ 1]);
+            tma_load_1d(dst + TILE_WORDS, B + tn * TILE_WORDS, TILE_WORDS * 8, &bars[buf ^ 1]);
+        }
+        uint32_t a[WD], b[WD], atop, btop;
+        const uint64_t u = t * MR_THREADS + tid;
+        if (t < nfull) {
+            mbar_wait(&bars[buf], (it >> 1) & 1);
+            const uint64_t *sa = tiles + (size_t)buf * 2 * TILE_WORDS + (size_t)tid * WF;
+            const uint64_t *sb = sa + TILE_WORDS;
+#pragma unroll
+            for (int j = 0; j < WD / 2; ++j) {
+                const uint64_t x = sa[j], y = sb[j];
+                a[2 * j] = (uint32_t)x; a[2 * j + 1] = (uint32_t)(x >> 32);
+                b[2 * j] = (uint32_t)y; b[2 * j + 1] = (uint32_t)(y >> 32);
+            }
+            atop = (uint32_t)sa[WD / 2] & 1u;
+            btop = (uint32_t)sb[WD / 2] & 1u;
+        } else { // ragged last tile: straight from global
+#pragma unroll
+            for (int j = 0; j < WD; ++j) a[j] = b[j] = 0;
+            atop = btop = 0;
+            if (u < n) {
+                const uint64_t *ga = A + u * WF, *gb = B + u * WF;
+#pragma unroll
+                for (int j = 0; j < WD / 2; ++j) {
+                    const uint64_t x = ga[j], y = gb[j];
+                    a[2 * j] = (uint32_t)x; a[2 * j + 1] = (uint32_t)(x >> 32);
+                    b[2 * j] = (uint32_t)y; b[2 * j + 1] = (uint32_t)(y >> 32);
+                }
+                atop = (uint32_t)ga[WD / 2] & 1u;
+                btop = (uint32_t)gb[WD / 2] & 1u;
+            }
+        }
+        uint32_t lowp[2 * WD];
+        clmul_regs<WD, WD>(a, b, lowp);
+        uint32_t pr[NP];
+#pragma unroll
+        for (int i = 0; i < 2 * WD; ++i) pr[i] = lowp[i];
+        const uint32_t ma = 0u - atop, mb = 0u - btop;
+#pragma unroll
+        for (int j = 0; j < WD; ++j) pr[WD + j] ^= (b[j] & ma) ^ (a[j] & mb);
+        pr[2 * WD] = atop & btop;
+        // fold words NP-1 .. WS down into the low WS words
+#pragma unroll
+        for (int i = NP - 1; i >= WS; --i) {
+            uint32_t dst[WS];
+#pragma unroll
+            for (int q = 0; q < WS; ++q) dst[q] = pr[i - WS + q];
+            fold_word<WS>(dst, pr[i], T);
+#pragma unroll
+            for (int q = 0; q < WS; ++q) pr[i - WS + q] = dst[q];
+        }
+        if (u < n) {
+            uint32_t *out = reinterpret_cast<uint32_t *>(O + u * (WS / 2));
+            if constexpr (WS % 4 == 0) {
+#pragma unroll
+                for (int q = 0; q < WS / 4; ++q)
+                    reinterpret_cast<uint4 *>(out)[q] = make_uint4(pr[4 * q], pr[4 * q + 1], pr[4 * q + 2], pr[4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < WS; ++q) out[q] = pr[q];
+            }
+        }
+        __syncthreads(); // everyone is done with tiles[buf] before it is refilled
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// K6  fused ripple-carry adder, one warp per value        reference common.rs:37-56
+//
+//   p_k = a_k + b_k, g_k = a_k * b_k, m_k = (1 + g_k) * p_k           (lane k, registers)
+//   c_0 = 0, c_{k+1} = m_k * c_k + g_k,  s_k = p_k + c_k             (serial over k)
+// which is the reference's  carry' = p*c + (a*b)*(p*c + 1)  regrouped with ring identities.
+// The long carry polynomial c_k lives in shared memory (two buffers); every lane owns tiles of
+// 8 output words of c_{k+1} and computes them completely (no write conflicts).  m_k is the
+// same for all lanes, so its bits are warp-uniform: zero bits are skipped by uniform branches.
+// Horner over the bit index s of m_k: acc = acc*X ^ sum_{j in B_s} c[r - j], with one halo
+// word below the tile so that the shift never needs a neighbour.
+// ----------------------------------------------------------------------------------------
+template <int WD> struct AdderCfg {
+    static constexpr int NP = WD + 1;      // words of p_k (bit D in the last)
+    static constexpr int NG = 2 * WD + 1;  // words of g_k
+    static constexpr int NM = 3 * WD + 1;  // words of m_k
+    static constexpr int TQ = 8;           // output words per tile
+    static constexpr int PAD = NM + 7;     // zero words in front of each carry buffer (window underflow)
+    __host__ __device__ static constexpr uint32_t carry_cap(uint32_t L) { // words, multiple of TQ
+        return (((3 * (L - 1) - 1) * WD + 1 + TQ - 1) / TQ) * TQ + TQ;
+    }
+    __host__ __device__ static constexpr uint32_t warp_words(uint32_t L) {
+        return L * (NP + NG + NM) + 2 * (PAD + carry_cap(L)) + 4;
+    }
+};
+
+template <int WD, int R>
+__device__ __forceinline__ void adder_step_tiles(const uint32_t *__restrict__ ccur, uint32_t *__restrict__ cnxt,
+                                                 const uint32_t *__restrict__ gk, uint32_t Bmine, uint32_t tile0,
+                                                 uint32_t ntiles, int lane) {
+    using C = AdderCfg<WD>;
+    constexpr int NM = C::NM, TQ = C::TQ, NW = NM + TQ; // window words per tile
+    uint32_t win[R][NW], acc[R][TQ + 1];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t t0 = (tile0 + lane + 32 * r) * TQ;
+        // win[y] = c[t0 - NM + y]; the buffer has PAD >= NM zero words in front, so no bounds checks
+        const uint32_t *src = ccur + (int)t0 - NM;
+#pragma unroll
+        for (int y = 0; y < NW; ++y) win[r][y] = src[y];
+#pragma unroll
+        for (int i = 0; i <= TQ; ++i) acc[r][i] = 0;
+    }
+#pragma unroll 1
+    for (int s = 31; s >= 0; --s) {
+        const uint32_t Bs = __shfl_sync(FULL, Bmine, s); // bit j set <=> bit s of m_k[j] set
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int i = TQ; i > 0; --i) acc[r][i] = __funnelshift_l(acc[r][i - 1], acc[r][i], 1);
+            acc[r][0] <<= 1;
+        }
+        // acc[i] is output word t0-1+i; it receives c[t0-1+i-j] = win[i + NM-1 - j]
+#pragma unroll
+        for (int jp = 0; jp + 1 < NM; jp += 2) {
+            const uint32_t sel = (Bs >> jp) & 3u;
+            if (sel == 3u) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int i = 0; i <= TQ; ++i) acc[r][i] ^= win[r][i + NM - 1 - jp] ^ win[r][i + NM - 2 - jp];
+            } else if (sel == 1u) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int i = 0; i <= TQ; ++i) acc[r][i] ^= win[r][i + NM - 1 - jp];
+            } else if (sel == 2u) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int i = 0; i <= TQ; ++i) acc[r][i] ^= win[r][i + NM - 2 - jp];
+            }
+        }
+        if constexpr (NM & 1) {
+            if ((Bs >> (NM - 1)) & 1u) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int i = 0; i <= TQ; ++i) acc[r][i] ^= win[r][i];
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t tile = tile0 + lane + 32 * r;
+        if (tile < ntiles) {
+            const uint32_t t0 = tile * TQ;
+            uint32_t o[TQ];
+#pragma unroll
+            for (int i = 0; i < TQ; ++i) {
+                const uint32_t x = t0 + i;
+                o[i] = acc[r][i + 1] ^ ((x < (uint32_t)C::NG) ? gk[x] : 0u);
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(cnxt + t0);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
+
+template <int WD>
+__global__ void __launch_bounds__(128) adder_fused_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
+                                                          uint64_t *__restrict__ O, uint64_t n, uint32_t L, Layout lo) {
+    using C = AdderCfg<WD>;
+    constexpr int WF = WD / 2 + 1;
+    constexpr int NP = C::NP, NG = C::NG, NM = C::NM, TQ = C::TQ;
+    extern __shared__ __align__(16) uint32_t smem32[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t v = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (v >= n) return;
+    const uint32_t cap = C::carry_cap(L);
+    uint32_t *base = smem32 + (size_t)warp * C::warp_words(L);
+    // carry buffers first (16-byte aligned: warp_words is a multiple of 4, PAD+cap multiple of ... see static_assert)
+    uint32_t *cbuf0 = base;                       // PAD zeros + cap words
+    uint32_t *cbuf1 = base + (C::PAD + cap);
+    uint32_t *P = base + 2 * (C::PAD + cap);      // L x NP
+    uint32_t *G = P + L * NP;                     // L x NG
+    uint32_t *M = G + L * NG;                     // L x NM
+    static_assert((C::PAD % 4) == 0, "carry buffers must stay 16-byte aligned");
+
+    for (uint32_t i = lane; i < 2 * (C::PAD + cap); i += 32) base[i] = 0;
+
+    // ---- stage 1: per-bit products, lane k owns bit k ------------------------------------
+    const uint64_t *Av = A + v * (uint64_t)L * WF, *Bv = B + v * (uint64_t)L * WF;
+    for (uint32_t k = lane; k < ((L + 31) & ~31u); k += 32) {
+        uint32_t a[WD], b[WD], p[WD], atop = 0, btop = 0;
+        const bool live = k < L;
+#pragma unroll
+        for (int j = 0; j < WD / 2; ++j) {
+            const uint64_t x = live ? __ldg(Av + (size_t)k * WF + j) : 0ull;
+            const uint64_t y = live ? __ldg(Bv + (size_t)k * WF + j) : 0ull;
+            a[2 * j] = (uint32_t)x; a[2 * j + 1] = (uint32_t)(x >> 32);
+            b[2 * j] = (uint32_t)y; b[2 * j + 1] = (uint32_t)(y >> 32);
+        }
+        if (live) {
+            atop = (uint32_t)__ldg(Av + (size_t)k * WF + WD / 2) & 1u;
+            btop = (uint32_t)__ldg(Bv + (size_t)k * WF + WD / 2) & 1u;
+        }
+#pragma unroll
+        for (int j = 0; j < WD; ++j) p[j] = a[j] ^ b[j];
+        const uint32_t ptop = atop ^ btop;
+        uint32_t g[2 * WD];
+        clmul_regs<WD, WD>(a, b, g);
+        const uint32_t ma = 0u - atop, mb = 0u - btop;
+#pragma unroll
+        for (int j = 0; j < WD; ++j) g[WD + j] ^= (b[j] & ma) ^ (a[j] & mb);
+        const uint32_t gtop = atop & btop; // coefficient of X^(2D)
+        uint32_t gp[3 * WD];
+        clmul_regs<2 * WD, WD>(g, p, gp);
+        const uint32_t mp = 0u - ptop, mg = 0u - gtop;
+#pragma unroll
+        for (int j = 0; j < 2 * WD; ++j) gp[WD + j] ^= g[j] & mp;
+#pragma unroll
+        for (int j = 0; j < WD; ++j) gp[2 * WD + j] ^= p[j] & mg;
+#pragma unroll
+        for (int j = 0; j < WD; ++j) gp[j] ^= p[j]; // m = p + g*p
+        gp[WD] ^= ptop;
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < WD; ++j) P[k * NP + j] = p[j];
+            P[k * NP + WD] = ptop;
+#pragma unroll
+            for (int j = 0; j < 2 * WD; ++j) G[k * NG + j] = g[j];
+            G[k * NG + 2 * WD] = gtop;
+#pragma unroll
+            for (int j = 0; j < 3 * WD; ++j) M[k * NM + j] = gp[j];
+            M[k * NM + 3 * WD] = gtop & ptop; // coefficient of X^(3D)
+        }
+    }
+    __syncwarp();
+
+    // ---- s_0 = p_0 ; c_1 = g_0 ------------------------------------------------------------
+    uint64_t *Ov = O + v * (uint64_t)lo.value_words;
+    for (uint32_t j = lane; j < lo.off[1] - lo.off[0]; j += 32) {
+        const uint32_t x0 = (2 * j < (uint32_t)NP) ? P[2 * j] : 0u, x1 = (2 * j + 1 < (uint32_t)NP) ? P[2 * j + 1] : 0u;
+        Ov[lo.off[0] + j] = (uint64_t)x0 | ((uint64_t)x1 << 32);
+    }
+    uint32_t *ccur = cbuf0 + C::PAD, *cnxt = cbuf1 + C::PAD;
+    for (uint32_t j = lane; j < (uint32_t)NG; j += 32) ccur[j] = G[j];
+    __syncwarp();
+
+    // ---- serial chain ---------------------------------------------------------------------
+    for (uint32_t k = 1; k < L; ++k) {
+        // s_k = p_k + c_k, coalesced 64-bit stores
+        {
+            const uint32_t wo = lo.off[k + 1] - lo.off[k];
+            uint64_t *dst = Ov + lo.off[k];
+            const uint32_t *pk = P + k * NP;
+            for (uint32_t j = lane; j < wo; j += 32) {
+                uint32_t x0 = ccur[2 * j], x1 = ccur[2 * j + 1];
+                if (2 * j < (uint32_t)NP) x0 ^= pk[2 * j];
+                if (2 * j + 1 < (uint32_t)NP) x1 ^= pk[2 * j + 1];
+                dst[j] = (uint64_t)x0 | ((uint64_t)x1 << 32);
+            }
+        }
+        if (k + 1 == L) break; // no carry out of the last bit (common.rs:47-49)
+        // transpose m_k: lane s gets the mask of words j whose bit s is set
+        uint32_t Bmine = 0;
+        {
+            const uint32_t *mk = M + k * NM;
+#pragma unroll
+            for (int j = 0; j < NM; ++j) Bmine |= ((mk[j] >> lane) & 1u) << j;
+        }
+        const uint32_t len_next = (3 * k + 2) * WD + 1;       // words of c_{k+1}
+        const uint32_t ntiles = (len_next + TQ - 1) / TQ;
+        const uint32_t *gk = G + k * NG;
+        uint32_t tile0 = 0;
+        while (tile0 < ntiles) {
+            const uint32_t left = ntiles - tile0;
+            if (left > 64) {
+                adder_step_tiles<WD, 3>(ccur, cnxt, gk, Bmine, tile0, ntiles, lane);
+                tile0 += 96;
+            } else if (left > 32) {
+                adder_step_tiles<WD, 2>(ccur, cnxt, gk, Bmine, tile0, ntiles, lane);
+                tile0 += 64;
+            } else {
+                adder_step_tiles<WD, 1>(ccur, cnxt, gk, Bmine, tile0, ntiles, lane);
+                tile0 += 32;
+            }
+        }
+        __syncwarp();
+        uint32_t *tsw = ccur; ccur = cnxt; cnxt = tsw;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// LOP3 issue-rate probe: the measured denominator of the integer-logic roofline.
+// 8 independent dependency chains per thread, 8 warps per CTA, 8 CTAs per SM.
+// ----------------------------------------------------------------------------------------
+constexpr int PEAK_ILP = 8;
+__global__ void __launch_bounds__(256) lop3_peak_kernel(uint32_t *sink, unsigned long long *clk, int iters, uint32_t seed) {
+    uint32_t x[PEAK_ILP], y[PEAK_ILP];
+#pragma unroll
+    for (int i = 0; i < PEAK_ILP; ++i) {
+        x[i] = seed + threadIdx.x * 7u + i;
+        y[i] = seed * 3u + i + blockIdx.x;
+    }
+    const uint32_t c = seed | 1u;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < PEAK_ILP; ++i) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y[i]), "r"(c));
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < PEAK_ILP; ++i) acc ^= x[i];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) clk[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
+} // namespace hmk

@@ -1,0 +1,199 @@
+/*
+ * hmgpu.h — C ABI of libhmgpu.so, the B200-native batched ciphertext engine for the
+ * GF(2)[X] hot path of mathisbot/homomorph-rust (crate `homomorph` v1.1.0).
+ *
+ * The reference has NO FFI/plugin interface; its only seams are
+ * Rust-level.  Each entry point below names the reference interface it replaces
+ * (file:line into the reference tree) so that a Rust shim can bind it 1:1 — the
+ * `extern "C"` block a maintainer would add is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; opaque handles; no exceptions/panics cross the ABI;
+ *   - every function returns an hm_status (0 = ok, negative = error mirroring the
+ *     reference's error enums / panics); hm_status_string() names it;
+ *   - a *batch* is n values x L bit-ciphertexts ("slots", LSB first — src/cipher.rs:180-185)
+ *     resident in HBM.  Slot k of every value has the same fixed width w[k] in 64-bit
+ *     words; words are the reference's own coefficient words: LSB-first, coefficient of
+ *     X^i is bit i%64 of word i/64 (src/polynomial.rs:144,172), zero padded above the
+ *     degree.  The canonical polynomial the reference would hold is (degree = highest set
+ *     bit, words[0 ..= degree/64]) — src/polynomial.rs:404-426 ignore anything above;
+ *   - host-side layout of a batch ("padded layout"): value-major, slot-minor, word-minor:
+ *         host[(v * value_words) + slot_offset[k] + j],  value_words = sum_k w[k];
+ *   - work is enqueued on the context's CUDA stream; calls that return data to host
+ *     memory synchronise that stream before returning;
+ *   - a context may be used by one host thread at a time; contexts are independent.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ *     with HM_ERR_CUDA.
+ */
+#ifndef HMGPU_H
+#define HMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hm_context hm_context; /* Context            — src/context.rs:301-305 */
+typedef struct hm_batch hm_batch;     /* Vec<Ciphered<T>>   — src/cipher.rs:126-130, device resident */
+
+typedef enum hm_status {
+    HM_OK = 0,
+    HM_ERR_INVALID_PARAMETERS = -1,  /* Parameters::new asserts            — src/context.rs:87-94   */
+    HM_ERR_PUBLIC_KEY_UNSET = -2,    /* ContextCryptoError::PublicKeyUnset — src/context.rs:41-52   */
+    HM_ERR_SECRET_KEY_UNSET = -3,    /* ContextCryptoError::SecretKeyUnset — src/context.rs:41-52   */
+    HM_ERR_OPERATION_REQUIREMENT = -4, /* OperationError::InvalidParameters — src/operations.rs:11-18 */
+    HM_ERR_INVALID_LENGTH = -5,      /* CipherError::InvalidCipheredLength — src/cipher.rs:17-24    */
+    HM_ERR_CUDA = -6,                /* device missing / CUDA runtime failure                       */
+    HM_ERR_UNSUPPORTED = -7,         /* shape outside what the kernels are built for                */
+    HM_ERR_INVALID_ARGUMENT = -8,    /* NULL pointer, mismatched batches, empty polynomial          */
+    HM_ERR_DIVIDE_BY_ZERO = -9       /* Polynomial::rem panic              — src/polynomial.rs:319-322 */
+} hm_status;
+
+/* Operation selectors = the marker types of src/impls/numbers.rs:7-25. */
+typedef enum hm_op {
+    HM_OP_AND = 0, /* HomomorphicAndGate         MIN_D_OVER_DELTA  2 — src/impls/numbers.rs:27-29 */
+    HM_OP_OR = 1,  /* HomomorphicOrGate                            2 — :31-33 */
+    HM_OP_XOR = 2, /* HomomorphicXorGate                           1 — :35-37 */
+    HM_OP_NOT = 3, /* HomomorphicNotGate                           1 — :39-41 */
+    HM_OP_ADD = 4, /* HomomorphicAddition                         21 — :43-45 */
+    HM_OP_MUL = 5  /* HomomorphicMultiplication                   64 — :47-50 */
+} hm_op;
+
+const char *hm_status_string(int status);
+/* Last CUDA error text recorded on this context (empty string if none). */
+const char *hm_last_error(const hm_context *ctx);
+/* Number of CUDA devices visible; 0 when there is no driver/GPU (never an error). */
+int hm_device_count(void);
+
+/* ---- Context / Parameters ------------------------------------------------------------
+ * Parameters::new + Context::new — src/context.rs:87-94, :341-347.  Rejects d, dp, delta or
+ * tau == 0 and delta >= d with HM_ERR_INVALID_PARAMETERS (the reference panics).
+ * `device` is the CUDA ordinal the context (keys, tables, stream, batches) lives on. */
+int hm_context_create(uint16_t d, uint16_t dp, uint16_t delta, uint16_t tau, int device, hm_context **out);
+/* Drop: zeroises the secret key, its derived tables and staging (src/context.rs:199-206). */
+void hm_context_destroy(hm_context *ctx);
+int hm_context_parameters(const hm_context *ctx, uint16_t *d, uint16_t *dp, uint16_t *delta, uint16_t *tau);
+/* Use a caller-owned CUDA stream (cudaStream_t) for all subsequent work; NULL = own stream. */
+int hm_context_set_stream(hm_context *ctx, void *cuda_stream);
+void *hm_context_stream(const hm_context *ctx);
+int hm_context_synchronize(hm_context *ctx);
+/* Counter of kernels this library has launched on this context (bench.py "gpu_launches"). */
+uint64_t hm_context_kernel_launches(const hm_context *ctx);
+/* CUDA ordinal the context lives on. */
+int hm_context_device(const hm_context *ctx);
+
+/* Context::set_secret_key(SecretKey::from_bytes(bytes)) — src/context.rs:153-155, :568-571.
+ * `bytes` is SecretKey::to_bytes(): little-endian u64 words (src/polynomial.rs:99-122).
+ * Clears the public key, like the reference.  Degree must equal d. */
+int hm_set_secret_key(hm_context *ctx, const uint8_t *bytes, size_t len);
+/* Context::set_public_key(PublicKey::from_bytes(..)) — src/context.rs:239-245, :592-595.
+ * polys[i]/lens[i] = PublicKey::to_bytes()[i]; n_polys must equal tau. */
+int hm_set_public_key(hm_context *ctx, const uint8_t *const *polys, const size_t *lens, size_t n_polys);
+int hm_has_secret_key(const hm_context *ctx);
+int hm_has_public_key(const hm_context *ctx);
+
+/* ---- Batches -------------------------------------------------------------------------- */
+size_t hm_batch_len(const hm_batch *b);          /* n values                                   */
+uint32_t hm_batch_bits(const hm_batch *b);       /* L bit-ciphertexts per value (Ciphered::len) */
+size_t hm_batch_value_words(const hm_batch *b);  /* sum of slot widths, in u64 words           */
+/* Copies the L slot widths (u64 words) into widths_out[0..L). */
+int hm_batch_slot_words(const hm_batch *b, uint32_t *widths_out);
+void *hm_batch_device_ptr(const hm_batch *b);    /* the padded layout, in HBM                   */
+void hm_batch_free(hm_context *ctx, hm_batch *b);
+/* Host <-> HBM in the padded layout described above (n * value_words u64 words).
+ * upload = what a shim does with Vec<CipheredBit> built by Ciphered::new_from_raw
+ * (src/cipher.rs:151-156); download = reading the polynomials back. */
+int hm_batch_upload(hm_context *ctx, size_t n, uint32_t L, const uint32_t *slot_words, const uint64_t *host,
+                    hm_batch **out);
+int hm_batch_download(hm_context *ctx, const hm_batch *b, uint64_t *host);
+/* Same as hm_batch_upload, but the caller states a degree bound per slot (>= the true degree of every
+ * polynomial in that slot); slot k is degree_bounds[k]/64+1 words wide.  Tight bounds keep the results of
+ * multiplications as narrow as the reference's (out len = (da+db)/64+1, src/polynomial.rs:264). */
+int hm_batch_upload_bounded(hm_context *ctx, size_t n, uint32_t L, const uint64_t *degree_bounds,
+                            const uint64_t *host, hm_batch **out);
+/* Copies the L per-slot degree bounds the engine tracks for this batch. */
+int hm_batch_slot_degree_bounds(const hm_batch *b, uint64_t *bounds_out);
+/* Page-locked host memory for the host-buffer entry points (hm_encrypt, hm_decrypt, hm_apply2_host,
+ * upload/download): pageable memory works too, but is staged by the driver. NULL on failure. */
+void *hm_host_alloc(size_t bytes);
+void hm_host_free(void *p);
+/* Device-resident duplicate (Ciphered::clone). */
+int hm_batch_clone(hm_context *ctx, const hm_batch *b, hm_batch **out);
+
+/* ---- Encrypt / decrypt ----------------------------------------------------------------
+ * Context::encrypt -> Ciphered::try_cipher -> CipheredBit::cipher for n integers at once —
+ * src/context.rs:463-471, src/cipher.rs:175-191, :99-115.
+ *   values : n * (L/8) bytes, each integer little endian (bincode fixint LE, src/cipher.rs:6-13,176)
+ *   L      : bits per value, multiple of 8 (u8 = 8, u32 = 32, ...)
+ *   masks  : the subset U for every bit, replacing getrandom (src/cipher.rs:92-97):
+ *            n * L * ceil(tau/8) bytes, value-major then bit-minor; polynomial T_i is included
+ *            iff masks[..][i/8] & (1 << (i%8))  (src/cipher.rs:106).
+ * `values`/`masks` are HOST pointers; the *_device variant takes device pointers. */
+int hm_encrypt(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, const uint8_t *masks, hm_batch **out);
+int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
+                      hm_batch **out);
+/* Context::decrypt -> Ciphered::try_decipher -> CipheredBit::decipher — src/context.rs:480-488,
+ * src/cipher.rs:217-250, :119-122.  Writes n * (L/8) bytes.  L % 8 != 0 -> HM_ERR_INVALID_LENGTH. */
+int hm_decrypt(hm_context *ctx, const hm_batch *b, uint8_t *values_out);
+int hm_decrypt_device(hm_context *ctx, const hm_batch *b, uint8_t *d_values_out);
+
+/* ---- Homomorphic operations -------------------------------------------------------------
+ * Context::apply2::<O, T>(&a, &b) — src/context.rs:515-527 — for every value of the batch:
+ * validate_operation (d >= MIN_D_OVER_DELTA * delta, src/context.rs:310-323, else
+ * HM_ERR_OPERATION_REQUIREMENT) then the circuit of src/impls/numbers/common.rs
+ * (gate_and :5-11, gate_or :13-19, gate_xor :21-27, add_internal :37-56,
+ * mul_unsigned_internal :66-105).  a and b must have the same n and L. */
+int hm_apply2(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch **out);
+/* Context::apply1::<HomomorphicNotGate, T>(&mut a) — src/context.rs:496-507, common.rs:29-35. In place. */
+int hm_apply1(hm_context *ctx, int op, hm_batch *a);
+/* The reference's `unsafe { O::apply(..) }` (src/operations.rs:81,140): same, without the
+ * parameter check. */
+int hm_apply2_unchecked(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch **out);
+/* Like hm_apply2 but writes into an existing batch `out` whose slot widths already equal
+ * hm_result_slot_words() of the operands (reuses the allocation; no cudaMalloc on the hot path). */
+int hm_apply2_into(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch *out);
+/* Same operation through the generic, slot-by-slot kernels in the reference's own evaluation order
+ * (no fused circuit kernel).  Results are identical; used to cross-check the fused adder. */
+int hm_apply2_generic(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch **out);
+/* MIN_D_OVER_DELTA of an op, or a negative status for an unknown op. */
+int hm_op_min_d_over_delta(int op);
+/* Slot widths (u64 words) of the result of `op` on operands of the given widths; used to size
+ * host buffers for hm_apply2_host. */
+int hm_result_slot_words(const hm_context *ctx, int op, uint32_t L, const uint32_t *a_words, const uint32_t *b_words,
+                         uint32_t *out_words);
+/* End-to-end convenience = upload a, upload b, apply2, download, with the copies overlapped
+ * with compute in chunks of values.  a/b/out are HOST buffers in the padded layout. */
+int hm_apply2_host(hm_context *ctx, int op, size_t n, uint32_t L, const uint32_t *a_words, const uint64_t *a_host,
+                   const uint32_t *b_words, const uint64_t *b_host, uint64_t *out_host);
+
+/* ---- Raw polynomial batches (L = 1) -------------------------------------------------------
+ * Polynomial::add / mul / rem over batches — src/polynomial.rs:190-213, :252-310, :316-365.
+ * rem is by the context's secret key S (the only divisor on the hot path, src/cipher.rs:120);
+ * mulrem is the fused `(a*b) mod S` unit of BASELINE.json's second metric. */
+int hm_poly_add(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out);
+int hm_poly_mul(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out);
+int hm_poly_rem(hm_context *ctx, const hm_batch *a, hm_batch **out);
+int hm_poly_mulrem(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out);
+
+/* ---- Measurement support ---------------------------------------------------------------------
+ * Runs a LOP3 issue-rate probe on the context's device and reports 32-bit LOP3 lane-operations per
+ * second (x32 = bit-MACs/s: one `r ^= a & m` is 32 AND-XOR pairs) and the SM clock seen meanwhile.
+ * This is the measured denominator of the integer-logic roofline of the multiply kernels. */
+int hm_measure_alu_peak(hm_context *ctx, double *lop3_lane_ops_per_s, double *sm_clock_mhz);
+
+/* ---- Host-side helpers (no GPU needed) ---------------------------------------------------- */
+/* Worst-case slot widths of a freshly encrypted value: (d+dp)/64+1 words per slot. */
+uint32_t hm_fresh_slot_words(const hm_context *ctx);
+/* v[k] = (X^k mod S)(0), k < nbits, as LSB-first u64 words: decryption is parity(C AND v),
+ * identical to rem + evaluate(false) (src/cipher.rs:119-122).  Needs the secret key. */
+int hm_decrypt_vector(const hm_context *ctx, size_t nbits, uint64_t *v_out);
+/* Canonical form of one slot: degree (highest set bit, 0 for the null polynomial,
+ * src/polynomial.rs:35-42) of a zero-padded word run. */
+size_t hm_poly_degree(const uint64_t *words, size_t n_words);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMGPU_H */

@@ -24,14 +24,35 @@ OP_AND, OP_OR, OP_XOR, OP_NOT, OP_ADD, OP_MUL, OP_MUL_SIGNED = range(7)
 POLY_ADD, POLY_MUL, POLY_REM = range(3)
 
 
+def _host_signature() -> str:
+    """The oracle is compiled with -march=native (mirroring the reference's target-cpu=native), so a
+    library built on another machine may not run here: rebuild when the CPU changes."""
+    import hashlib
+
+    try:
+        with open("/proc/cpuinfo") as f:
+            lines = [l for l in f if l.startswith(("model name", "flags"))][:2]
+    except OSError:
+        lines = []
+    return hashlib.sha256("".join(lines).encode()).hexdigest()
+
+
 def build(force: bool = False) -> str:
     """Compile libhmoracle.so with the committed Makefile (gcc -O3 -march=native -flto)."""
     src = os.path.join(_HERE, "hm_oracle.c")
+    stamp = _LIB_PATH + ".host"
+    sig = _host_signature()
     stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(
         os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "hm_oracle.h"))
     )
+    try:
+        stale = stale or open(stamp).read().strip() != sig
+    except OSError:
+        stale = True
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B", "libhmoracle.so"], check=True, capture_output=True)
+        with open(stamp, "w") as f:
+            f.write(sig)
     return _LIB_PATH
 
 
@@ -42,8 +63,7 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        build()
+    build()
     try:
         L = C.CDLL(_LIB_PATH)
     except OSError:

@@ -19,3 +19,5 @@ def oracle():
     hmoracle.build()
     hmoracle.lib()
     return hmoracle
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

@@ -1,0 +1,50 @@
+"""Shared helpers for the parity tests: seeded keys/masks for BOTH the oracle and the engine."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def keys(oracle, d, dp, delta, tau, seed):
+    """Oracle key pair + the same keys as the byte formats the C ABI takes
+    (SecretKey::to_bytes / PublicKey::to_bytes, src/polynomial.rs:99-105)."""
+    rng = np.random.default_rng(seed)
+    sk, pk = oracle.keygen(d, dp, delta, tau, rng)
+    sk_bytes = sk.words(0).astype("<u8").tobytes()
+    pk_bytes = [pk.words(i).astype("<u8").tobytes() for i in range(len(pk))]
+    return sk, pk, sk_bytes, pk_bytes
+
+
+def engine_context(hm, d, dp, delta, tau, sk_bytes, pk_bytes, device=0):
+    ctx = hm.Context(hm.Parameters(d, dp, delta, tau), device=device)
+    ctx.set_secret_key(hm.SecretKey.from_bytes(sk_bytes))
+    ctx.set_public_key(hm.PublicKey.from_bytes(pk_bytes))
+    return ctx
+
+
+def oracle_encrypt(oracle, pk, values: np.ndarray, masks: np.ndarray):
+    nbytes = values.dtype.itemsize
+    data = np.frombuffer(values.astype(values.dtype.newbyteorder("<")).tobytes(), dtype=np.uint8)
+    ct, _ = oracle.encrypt(pk, data, nbytes, masks, threads=oracle.max_threads())
+    return ct
+
+
+def expected_padded(polyvec, n, widths) -> np.ndarray:
+    """Oracle polynomials (value-major, slot-minor) laid out like an engine batch."""
+    L = len(widths)
+    off = np.concatenate([[0], np.cumsum(widths)]).astype(int)
+    out = np.zeros((n, off[-1]), dtype=np.uint64)
+    for v in range(n):
+        for k in range(L):
+            w = polyvec.words(v * L + k)
+            if w.size > widths[k]:
+                assert not np.any(w[widths[k]:]), "oracle polynomial exceeds the engine's slot width"
+                w = w[: widths[k]]
+            out[v, off[k] : off[k] + w.size] = w
+    return out
+
+
+def random_polys(rng, n, nwords, top_bits=64) -> np.ndarray:
+    a = rng.integers(0, 1 << 63, size=(n, nwords), dtype=np.uint64) * 2 + rng.integers(0, 2, size=(n, nwords), dtype=np.uint64)
+    if top_bits < 64:
+        a[:, -1] &= np.uint64((1 << top_bits) - 1)
+    return a

@@ -1,0 +1,232 @@
+"""GPU parity: the CUDA engine (through the C ABI / Python mirror) against the CPU oracle, bit for bit.
+
+Reference behaviours covered: CipheredBit::cipher/decipher (src/cipher.rs:99-122), try_cipher /
+try_decipher ordering (:175-250), the gates and circuits of src/impls/numbers/common.rs:5-105,
+Polynomial::add/mul/rem (src/polynomial.rs:190-365).
+"""
+import numpy as np
+import pytest
+
+from helpers import engine_context, expected_padded, keys, oracle_encrypt, random_polys
+
+pytestmark = pytest.mark.gpu
+
+CONFIG_A = (128, 128, 1, 128)
+CONFIG_B = (512, 512, 8, 256)
+
+
+@pytest.fixture(scope="module")
+def hm():
+    import homomorph_rust_b200 as h
+
+    assert h.lib().hm_device_count() > 0, "no CUDA device: the GPU tests must not silently pass"
+    return h
+
+
+def setup(oracle, hm, params, seed):
+    sk, pk, skb, pkb = keys(oracle, *params, seed)
+    return sk, pk, engine_context(hm, *params, skb, pkb)
+
+
+def masks_for(rng, n, L, tau):
+    return rng.integers(0, 256, size=n * L * ((tau + 7) // 8), dtype=np.uint8)
+
+
+@pytest.mark.parametrize(
+    "params,dtype,n",
+    [
+        (CONFIG_A, np.uint32, 700),  # 22 400 bit-cts: full tiles + ragged tail of the table kernel
+        (CONFIG_A, np.uint8, 37),
+        (CONFIG_B, np.uint32, 130),
+        ((64, 32, 8, 32), np.uint8, 50),   # src/cipher.rs:277
+        ((64, 32, 8, 32), np.uint64, 9),
+        ((6, 3, 2, 5), np.uint8, 20),      # doctest parameters, tau not a multiple of 8
+        ((32, 16, 16, 16), np.uint16, 11),
+    ],
+)
+def test_encrypt_decrypt(oracle, hm, params, dtype, n):
+    rng = np.random.default_rng(hash((params, n)) % 2**32)
+    sk, pk, ctx = setup(oracle, hm, params, 5)
+    L = np.dtype(dtype).itemsize * 8
+    values = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    masks = masks_for(rng, n, L, params[3])
+    ct = ctx.encrypt(values, masks)
+    assert ct.bits == L and len(ct) == n  # len == T::BITS, src/cipher.rs:286,292
+    want = oracle_encrypt(oracle, pk, values, masks)
+    got = ct.to_host()
+    np.testing.assert_array_equal(got, expected_padded(want, n, ct.slot_words()))
+    dec = ctx.decrypt(ct)
+    odec, _ = oracle.decrypt(sk, want, L)
+    np.testing.assert_array_equal(dec.view(np.uint8), odec)
+    # δ small enough for a fresh ciphertext to decrypt to its plaintext in these parameter sets
+    if params[2] * 2 <= params[0]:
+        np.testing.assert_array_equal(dec, values)
+
+
+def test_encrypt_empty_and_errors(oracle, hm):
+    sk, pk, skb, pkb = keys(oracle, *CONFIG_A, 1)
+    ctx = hm.Context(hm.Parameters(*CONFIG_A))
+    with pytest.raises(hm.PublicKeyUnset):
+        ctx.encrypt(np.zeros(1, dtype=np.uint8))
+    ctx.set_public_key(hm.PublicKey.from_bytes(pkb))
+    ct = ctx.encrypt(np.zeros(0, dtype=np.uint32))
+    assert len(ct) == 0 and ct.bits == 32
+    one = ctx.encrypt(np.array([7], dtype=np.uint8), rng=np.random.default_rng(0))
+    with pytest.raises(hm.SecretKeyUnset):
+        ctx.decrypt(one)
+    ctx.set_secret_key(hm.SecretKey.from_bytes(skb))
+    assert ctx.get_public_key() is None  # set_secret_key clears the public key, src/context.rs:657-667
+    with pytest.raises(hm.PublicKeyUnset):
+        ctx.encrypt(np.zeros(1, dtype=np.uint8))
+    assert int(ctx.decrypt(one)[0]) == 7
+    assert ctx.decrypt(ct).size == 0
+
+
+@pytest.mark.parametrize("params", [(32, 16, 16, 16), (32, 8, 1, 8), CONFIG_A])
+def test_gates(oracle, hm, params):
+    rng = np.random.default_rng(12)
+    sk, pk, ctx = setup(oracle, hm, params, 9)
+    n, L = 33, 8
+    a = rng.integers(0, 256, size=n, dtype=np.uint8)
+    b = rng.integers(0, 256, size=n, dtype=np.uint8)
+    a[0], b[0] = 0b1010, 0b1100  # uint.rs:109-174
+    ma, mb = masks_for(rng, n, L, params[3]), masks_for(rng, n, L, params[3])
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
+    for op, oop in [(hm.HomomorphicAndGate, oracle.OP_AND), (hm.HomomorphicOrGate, oracle.OP_OR), (hm.HomomorphicXorGate, oracle.OP_XOR)]:
+        if params[0] < op.MIN_D_OVER_DELTA * params[2]:
+            with pytest.raises(hm.OperationError):
+                ctx.apply2(op, ca, cb)
+            continue
+        r = ctx.apply2(op, ca, cb)
+        want, _ = oracle.apply(oop, oa, ob, L)
+        np.testing.assert_array_equal(r.to_host(), expected_padded(want, n, r.slot_words()))
+        od, _ = oracle.decrypt(sk, want, L)
+        np.testing.assert_array_equal(ctx.decrypt(r).view(np.uint8), od)
+    c = ca.clone()
+    ctx.apply1(hm.HomomorphicNotGate, c)
+    want, _ = oracle.apply(oracle.OP_NOT, oa, None, L)
+    np.testing.assert_array_equal(c.to_host(), expected_padded(want, n, c.slot_words()))
+    if params[2] == 1:
+        assert int(ctx.decrypt(c)[0]) == 0b1111_0101  # uint.rs:165-168
+
+
+@pytest.mark.parametrize("dtype,n", [(np.uint32, 40), (np.uint8, 70), (np.uint16, 9)])
+def test_add_fused_config_a(oracle, hm, dtype, n):
+    """HomomorphicAddition at d=d'=128 (fused ripple-carry kernel) — common.rs:37-56."""
+    rng = np.random.default_rng(n)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 21)
+    L = np.dtype(dtype).itemsize * 8
+    a = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    b = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    a[:3] = [22, np.iinfo(dtype).max, 0]
+    b[:3] = [20, 240, 0]
+    ma, mb = masks_for(rng, n, L, 128), masks_for(rng, n, L, 128)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    r = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+    oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
+    want, _ = oracle.apply(oracle.OP_ADD, oa, ob, L, threads=oracle.max_threads())
+    widths = r.slot_words()
+    D = 256
+    assert list(widths) == [D // 64 + 1] + [((3 * k - 1) * D) // 64 + 1 for k in range(1, L)]
+    got = r.to_host()
+    np.testing.assert_array_equal(got, expected_padded(want, n, widths))
+    # the generic slot-by-slot path in the reference's own evaluation order gives the same polynomials
+    g = ctx.apply2(hm.HomomorphicAddition, ca, cb, generic=True)
+    np.testing.assert_array_equal(g.to_host(), got)
+    # decrypt after add
+    dec = ctx.decrypt(r)
+    od, _ = oracle.decrypt(sk, want, L)
+    np.testing.assert_array_equal(dec.view(np.uint8), od)
+    assert int(dec[0]) == 42  # uint.rs:186-190
+
+
+@pytest.mark.parametrize("params,dtype", [((64, 16, 1, 16), np.uint8), ((64, 16, 1, 16), np.uint16), ((32, 8, 1, 8), np.uint8), (CONFIG_B, np.uint8)])
+def test_add_generic(oracle, hm, params, dtype):
+    """uint.rs:176-208 at (64,16,1,16): 22+20=42, 255+240=239 (wrap), random pairs."""
+    rng = np.random.default_rng(4)
+    sk, pk, ctx = setup(oracle, hm, params, 33)
+    n, L = 6, np.dtype(dtype).itemsize * 8
+    a = rng.integers(0, np.iinfo(dtype).max // 2, size=n, dtype=dtype)
+    b = rng.integers(0, np.iinfo(dtype).max // 2, size=n, dtype=dtype)
+    a[:2], b[:2] = [22, 255], [20, 240]
+    ma, mb = masks_for(rng, n, L, params[3]), masks_for(rng, n, L, params[3])
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    r = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+    oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
+    want, _ = oracle.apply(oracle.OP_ADD, oa, ob, L)
+    np.testing.assert_array_equal(r.to_host(), expected_padded(want, n, r.slot_words()))
+    od, _ = oracle.decrypt(sk, want, L)
+    np.testing.assert_array_equal(ctx.decrypt(r).view(np.uint8), od)
+    if params == (64, 16, 1, 16) and dtype == np.uint8:
+        assert int(ctx.decrypt(r)[0]) == 42
+
+
+@pytest.mark.parametrize("params", [(128, 64, 1, 64), CONFIG_A])
+def test_mul_u8(oracle, hm, params):
+    """HomomorphicMultiplication on u8 — common.rs:66-105; uint.rs:255-293 at (128,64,1,64)."""
+    rng = np.random.default_rng(8)
+    sk, pk, ctx = setup(oracle, hm, params, 44)
+    a = np.array([6, 0, 255, 11, 3], dtype=np.uint8)
+    b = np.array([7, 151, 240, 19, 200], dtype=np.uint8)
+    n, L = a.size, 8
+    ma, mb = masks_for(rng, n, L, params[3]), masks_for(rng, n, L, params[3])
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    r = ctx.apply2(hm.HomomorphicMultiplication, ca, cb)
+    oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
+    want, _ = oracle.apply(oracle.OP_MUL, oa, ob, L, threads=oracle.max_threads())
+    np.testing.assert_array_equal(r.to_host(), expected_padded(want, n, r.slot_words()))
+    dec = ctx.decrypt(r)
+    od, _ = oracle.decrypt(sk, want, L)
+    np.testing.assert_array_equal(dec.view(np.uint8), od)
+    assert list(dec[:3]) == [42, 0, 16]  # uint.rs:264-292
+
+
+def test_mul_requirement(oracle, hm):
+    sk, pk, ctx = setup(oracle, hm, (64, 16, 4, 16), 3)
+    c = ctx.encrypt(np.array([1], dtype=np.uint8), rng=np.random.default_rng(1))
+    with pytest.raises(hm.OperationError) as e:  # src/context.rs:310-323
+        ctx.apply2(hm.HomomorphicMultiplication, c, c)
+    assert e.value.required_min_d_over_delta == 64 and e.value.actual_d == 64 and e.value.actual_delta == 4
+
+
+@pytest.mark.parametrize("wa,wb", [(1, 1), (5, 5), (2, 9), (17, 17), (40, 3), (9, 361)])
+def test_poly_mul_rem(oracle, hm, wa, wb):
+    """Polynomial::mul / rem on raw batches (src/polynomial.rs:252-365), any widths."""
+    rng = np.random.default_rng(wa * 1000 + wb)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 2)
+    n = 45
+    A, B = random_polys(rng, n, wa), random_polys(rng, n, wb)
+    A[0] = 0  # null polynomial (src/polynomial.rs:257-261)
+    B[1] = 0
+    A[2, :] = 0
+    A[2, 0] = 1  # the constant 1
+    ba, bb = ctx.upload(A, [wa]), ctx.upload(B, [wb])
+    prod = ctx.poly_mul(ba, bb)
+    want = oracle.poly_binop(oracle.POLY_MUL, oracle.PolyVec.from_padded(A), oracle.PolyVec.from_padded(B))
+    np.testing.assert_array_equal(prod.to_host(), expected_padded(want, n, prod.slot_words()))
+    rem = ctx.poly_rem(prod)
+    wantr = oracle.poly_binop(oracle.POLY_REM, want, sk)
+    np.testing.assert_array_equal(rem.to_host(), expected_padded(wantr, n, rem.slot_words()))
+    assert list(rem.slot_words()) == [2]  # degree < 128
+    s = ctx.poly_add(ba, bb)
+    wants = oracle.poly_binop(oracle.POLY_ADD, oracle.PolyVec.from_padded(A), oracle.PolyVec.from_padded(B))
+    np.testing.assert_array_equal(s.to_host(), expected_padded(wants, n, s.slot_words()))
+
+
+@pytest.mark.parametrize("params,n", [(CONFIG_A, 1000), (CONFIG_A, 128 * 7), (CONFIG_B, 200), ((64, 32, 8, 32), 77), ((6, 3, 2, 5), 30)])
+def test_mulrem_fresh(oracle, hm, params, n):
+    """The BASELINE `mul+rem` unit on pairs of fresh ciphertexts (fused kernel at config A)."""
+    rng = np.random.default_rng(n)
+    sk, pk, ctx = setup(oracle, hm, params, 6)
+    va = rng.integers(0, 256, size=(n + 7) // 8, dtype=np.uint8)
+    vb = rng.integers(0, 256, size=(n + 7) // 8, dtype=np.uint8)
+    ma, mb = masks_for(rng, va.size, 8, params[3]), masks_for(rng, vb.size, 8, params[3])
+    ca, cb = ctx.encrypt(va, ma), ctx.encrypt(vb, mb)
+    r = ctx.poly_mulrem(ca, cb)
+    oa, ob = oracle_encrypt(oracle, pk, va, ma), oracle_encrypt(oracle, pk, vb, mb)
+    want, _ = oracle.poly_mulrem(oa, ob, sk, threads=oracle.max_threads())
+    np.testing.assert_array_equal(r.to_host(), expected_padded(want, va.size, r.slot_words()))
+    # separate mul then rem agrees with the fused kernel
+    two = ctx.poly_rem(ctx.poly_mul(ca, cb))
+    np.testing.assert_array_equal(two.to_host(), r.to_host())
