@@ -122,4 +122,5 @@ def exported_symbols():
     import re
 
     hdr = open(os.path.join(_HERE, "..", "include", "hmgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)  # declarations only, not prose
     return sorted(set(re.findall(r"\b(hm_[a-z0-9_]+)\s*\(", hdr)))

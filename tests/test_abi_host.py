@@ -1,0 +1,102 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol of include/hmgpu.h,
+argument validation that needs no GPU, and the host-side mirror of the reference API (keys, parameters)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import homomorph_rust_b200 as hm
+from homomorph_rust_b200 import _native as N
+
+
+def test_library_exports_every_declared_symbol():
+    lib = hm.lib()
+    names = N.exported_symbols()
+    assert len(names) >= 45
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/hmgpu.h but not exported by libhmgpu.so"
+
+
+def test_status_strings_and_requirements():
+    lib = hm.lib()
+    assert lib.hm_status_string(0) == b"ok"
+    assert b"divide by zero" in lib.hm_status_string(N.HM_ERR_DIVIDE_BY_ZERO)
+    # MIN_D_OVER_DELTA, reference src/impls/numbers.rs:27-50
+    assert [lib.hm_op_min_d_over_delta(op) for op in range(6)] == [2, 2, 1, 1, 21, 64]
+    assert lib.hm_op_min_d_over_delta(17) == N.HM_ERR_INVALID_ARGUMENT
+    for op, want in [(hm.HomomorphicAndGate, 2), (hm.HomomorphicOrGate, 2), (hm.HomomorphicXorGate, 1),
+                     (hm.HomomorphicNotGate, 1), (hm.HomomorphicAddition, 21), (hm.HomomorphicMultiplication, 64)]:
+        assert op.MIN_D_OVER_DELTA == want == lib.hm_op_min_d_over_delta(op.code)
+
+
+def test_parameter_validation_needs_no_gpu():
+    lib = hm.lib()
+    h = C.c_void_p()
+    # Parameters::new asserts (src/context.rs:87-94; tests :602-613) are checked before the device is touched
+    for bad in [(0, 1, 1, 1), (8, 0, 1, 1), (8, 1, 0, 1), (8, 1, 1, 0), (8, 4, 8, 4), (8, 4, 9, 4)]:
+        assert lib.hm_context_create(*bad, 0, C.byref(h)) == N.HM_ERR_INVALID_PARAMETERS
+    for bad in [(0, 1, 1, 1), (8, 4, 8, 4)]:
+        with pytest.raises(ValueError):
+            hm.Parameters(*bad)
+    p = hm.Parameters.new(6, 3, 2, 5)  # doctest parameters, src/context.rs:25
+    assert (p.d(), p.dp(), p.delta(), p.tau()) == (6, 3, 2, 5)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute path fails loudly (HM_ERR_CUDA), it never computes on the host."""
+    lib = hm.lib()
+    if lib.hm_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    assert lib.hm_context_create(128, 128, 1, 128, 0, C.byref(h)) == N.HM_ERR_CUDA
+    with pytest.raises(hm.EngineError):
+        hm.Context(hm.Parameters(128, 128, 1, 128))
+
+
+def test_poly_degree_helper():
+    lib = hm.lib()
+    u64p = C.POINTER(C.c_uint64)
+
+    def deg(words):
+        a = np.asarray(words, dtype=np.uint64)
+        return lib.hm_poly_degree(a.ctypes.data_as(u64p), a.size)
+
+    # src/polynomial.rs:440-449
+    assert deg([0b1]) == 0 and deg([0b10]) == 1 and deg([0b1001]) == 3
+    assert deg([0, 1]) == 64 and deg([0, 0]) == 0 and deg([1 << 63, 0, 0]) == 63
+
+
+class _ByteStream:
+    """numpy-Generator stand-in that serves a fixed byte string (so two keygens can share one stream)."""
+
+    def __init__(self, data: bytes):
+        self.data, self.pos = data, 0
+
+    def integers(self, lo, hi, size, dtype):
+        out = np.frombuffer(self.data[self.pos : self.pos + size], dtype=np.uint8)
+        self.pos += size
+        return out
+
+
+@pytest.mark.parametrize("params", [(128, 128, 1, 128), (64, 32, 8, 32), (6, 3, 2, 5), (512, 512, 8, 16), (100, 70, 3, 9)])
+def test_host_keygen_matches_oracle(oracle, params):
+    """SecretKey::random / PublicKey::random (src/context.rs:160-162, :249-261) of the host mirror vs the oracle."""
+    d, dp, delta, tau = params
+    L = oracle.lib()
+    rng = np.random.default_rng(sum(params))
+    sk_rnd = rng.integers(0, 256, size=L.orc_random_bytes_needed(d), dtype=np.uint8).tobytes()
+    pk_rnd = rng.integers(0, 256, size=L.orc_keygen_pk_bytes_needed(dp, delta, tau), dtype=np.uint8).tobytes()
+    u8p = C.POINTER(C.c_uint8)
+    a1 = np.frombuffer(sk_rnd, dtype=np.uint8).copy()
+    a2 = np.frombuffer(pk_rnd, dtype=np.uint8).copy()
+    osk = oracle.PolyVec(L.orc_keygen_sk(d, a1.ctypes.data_as(u8p)))
+    opk = oracle.PolyVec(L.orc_keygen_pk(dp, delta, tau, osk._h, a2.ctypes.data_as(u8p)))
+    sk = hm.SecretKey.random(d, _ByteStream(sk_rnd))
+    pk = hm.PublicKey.random(dp, delta, tau, sk, _ByteStream(pk_rnd))
+    assert sk.to_bytes() == osk.words(0).astype("<u8").tobytes()
+    assert len(pk) == tau
+    for i, row in enumerate(pk.to_bytes()):
+        assert row == opk.words(i).astype("<u8").tobytes()
+    # key byte round trips, src/context.rs:616-635
+    assert hm.SecretKey.from_bytes(sk.to_bytes()).to_bytes() == sk.to_bytes()
+    assert hm.PublicKey.from_bytes(pk.to_bytes()).to_bytes() == pk.to_bytes()
