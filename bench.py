@@ -287,41 +287,53 @@ def run_ours(args, rank, local_rank, world):
 
         hbm_peak, _ = measured_peaks()
         # mul+rem on fresh pairs: every slot of (ca, cb) is one pair -> n*32 pairs per launch
-        keep = []
+        mr = ctx.poly_mulrem(ca, cb)
         def mulrem():
-            keep.clear(); keep.append(ctx.poly_mulrem(ca, cb))
+            rc = lib.hm_poly_mulrem_into(ctx._h, ca._h, cb._h, mr._h)
+            assert rc == 0, rc
         s = timed(mulrem)
         pairs = n * L
+        lane_ops = C.c_double(0.0)
+        lib.hm_measure_alu_peak(ctx._h, C.byref(lane_ops), None)
         extra["mulrem"] = {"metric": "GF(2)[X] mul+rem/s (d=d'=128)", "value": pairs / s, "unit": "mul+rem/s",
-                           "pairs_per_launch": pairs, "ms": s * 1e3,
-                           "hbm_GBps": pairs * BYTES_PER_MULREM / s / 1e9, "bitmac_per_s": pairs * BITMACS_PER_MULREM / s}
-        keep.clear()
+                           "kernel": "mulrem_fresh_kernel<8,4>", "pairs_per_launch": pairs, "ms": s * 1e3,
+                           "hbm_GBps": pairs * BYTES_PER_MULREM / s / 1e9, "hbm_frac": pairs * BYTES_PER_MULREM / s / 1e9 / hbm_peak,
+                           "Tbitmac_per_s": pairs * BITMACS_PER_MULREM / s / 1e12,
+                           "alu_frac": pairs * BITMACS_PER_MULREM / s / (lane_ops.value * 32.0)}
+        mr.free()
         # decrypt after add (HBM bound: 46 912 B per value)
         dout = torch.empty(n * 4, dtype=torch.uint8, device=f"cuda:{local_rank}")
         s = timed(lambda: lib.hm_decrypt_device(ctx._h, out._h, dout.data_ptr()))
-        extra["decrypt_after_add"] = {"value": n / s, "unit": "u32/s", "ms": s * 1e3, "hbm_GBps": n * 46912 / s / 1e9,
-                                      "hbm_frac": n * 46912 / s / 1e9 / hbm_peak}
-        s = timed(lambda: lib.hm_decrypt_device(ctx._h, ca._h, dout.data_ptr()))
-        extra["decrypt_fresh"] = {"value": n / s, "unit": "u32/s", "ms": s * 1e3, "hbm_GBps": n * 1280 / s / 1e9,
-                                  "hbm_frac": n * 1280 / s / 1e9 / hbm_peak}
-        # encrypt with values + masks already in HBM
+        extra["decrypt_after_add"] = {"value": n / s, "unit": "u32/s", "kernel": "decrypt_slots_kernel", "ms": s * 1e3,
+                                      "hbm_GBps": n * 46912 / s / 1e9, "hbm_frac": n * 46912 / s / 1e9 / hbm_peak}
+        s = timed(lambda: lib.hm_decrypt_device(ctx._h, ca._h, dout.data_ptr()), reps=20)
+        extra["decrypt_fresh"] = {"value": n / s, "unit": "u32/s", "kernel": "decrypt_uniform_kernel", "ms": s * 1e3,
+                                  "hbm_GBps": n * 1280 / s / 1e9, "hbm_frac": n * 1280 / s / 1e9 / hbm_peak,
+                                  "note": "320 MiB of ciphertext per launch (> 126 MB L2)"}
+        # encrypt with values + masks already in HBM, into an existing batch
         g = np.random.default_rng(1)
         dm = torch.from_numpy(np.frombuffer(g.bytes(n * L * 16), dtype=np.uint8).copy()).to(f"cuda:{local_rank}")
         dv = torch.from_numpy(a.view(np.uint8).copy()).to(f"cuda:{local_rank}")
-        hold = []
+        ce = ca.clone()
         def encd():
-            for hnd in hold:
-                lib.hm_batch_free(ctx._h, hnd)
-            hold.clear()
-            o = C.c_void_p()
-            rc = lib.hm_encrypt_device(ctx._h, dv.data_ptr(), n, L, dm.data_ptr(), C.byref(o))
-            assert rc == 0
-            hold.append(o)
-        s = timed(encd)
-        extra["encrypt"] = {"value": n / s, "unit": "u32/s", "ms": s * 1e3, "hbm_GBps": n * 1792 / s / 1e9,
-                            "hbm_frac": n * 1792 / s / 1e9 / hbm_peak}
-        for hnd in hold:
-            lib.hm_batch_free(ctx._h, hnd)
+            rc = lib.hm_encrypt_device_into(ctx._h, dv.data_ptr(), n, L, dm.data_ptr(), ce._h)
+            assert rc == 0, rc
+        s = timed(encd, reps=20)
+        extra["encrypt"] = {"value": n / s, "unit": "u32/s", "kernel": "encrypt_tab_kernel<5,4,8>", "ms": s * 1e3,
+                            "hbm_GBps": n * 1792 / s / 1e9, "hbm_frac": n * 1792 / s / 1e9 / hbm_peak}
+        ce.free()
+        # PCIe copy rates of this box (the ceiling of every host-buffer call)
+        hp = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+        dp_ = torch.empty(1 << 30, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        for name, src, dst in (("h2d_GBps", hp, dp_), ("d2h_GBps", dp_, hp)):
+            dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            extra[name] = 3 * (1 << 30) / (time.perf_counter() - t0) / 1e9
+        del hp, dp_
+        extra["e2e_pcie_frac"] = (e2e_value / world) * 46912 / 1e9 / extra["d2h_GBps"]
 
     # ---- roofline of the dominant kernel (adder_fused_kernel: one launch per step) ---------------------------
     roofline = roofline_hbm = None

@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
         "hm_host_free": (None, [vp]),
         "hm_encrypt": (C.c_int, [vp, vp, sz, C.c_uint32, vp, C.POINTER(vp)]),
         "hm_encrypt_device": (C.c_int, [vp, vp, sz, C.c_uint32, vp, C.POINTER(vp)]),
+        "hm_encrypt_device_into": (C.c_int, [vp, vp, sz, C.c_uint32, vp, vp]),
         "hm_decrypt": (C.c_int, [vp, vp, vp]),
         "hm_decrypt_device": (C.c_int, [vp, vp, vp]),
         "hm_apply2": (C.c_int, [vp, C.c_int, vp, vp, C.POINTER(vp)]),
@@ -102,6 +103,7 @@ def lib() -> C.CDLL:
         "hm_poly_mul": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
         "hm_poly_rem": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "hm_poly_mulrem": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
+        "hm_poly_mulrem_into": (C.c_int, [vp, vp, vp, vp]),
         "hm_fresh_slot_words": (C.c_uint32, [vp]),
         "hm_decrypt_vector": (C.c_int, [vp, sz, u64p]),
         "hm_poly_degree": (sz, [u64p, sz]),

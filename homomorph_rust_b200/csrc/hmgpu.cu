@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -659,6 +660,8 @@ void hm_host_free(void *p) {
 }
 
 // ---- encrypt / decrypt ------------------------------------------------------------------------
+static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks, hm_batch *b);
+
 int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
                       hm_batch **out) {
     if (!ctx || !out || ((!d_values || !d_masks) && n)) return HM_ERR_INVALID_ARGUMENT;
@@ -669,11 +672,28 @@ int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32
     hm_batch *b = new_batch(ctx, n, L, degb.data());
     if (!b) return HM_ERR_INVALID_ARGUMENT;
     int rc = alloc_batch(ctx, b);
+    if (rc == HM_OK) rc = encrypt_exec(ctx, d_values, n, L, d_masks, b);
     if (rc != HM_OK) {
-        delete b;
+        hm_batch_free(ctx, b);
         return rc;
     }
     *out = b;
+    return HM_OK;
+}
+
+int hm_encrypt_device_into(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
+                           hm_batch *out) {
+    if (!ctx || !out || ((!d_values || !d_masks) && n)) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_pk) return HM_ERR_PUBLIC_KEY_UNSET;
+    if (out->n != n || out->L != L || L % 8 != 0) return HM_ERR_INVALID_ARGUMENT;
+    for (uint32_t k = 0; k < L; ++k)
+        if (out->w[k] != ctx->wf) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    out->degb.assign(L, ctx->fresh_deg);
+    return encrypt_exec(ctx, d_values, n, L, d_masks, out);
+}
+
+static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks, hm_batch *b) {
     if (n == 0) return HM_OK;
     hmk::EncParams p;
     p.values = d_values;
@@ -1149,7 +1169,8 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                 int warps = (int)std::min<size_t>(4, ctx->smem_optin / per_warp);
                 if (warps < 1) warps = 1;
                 const size_t smem = per_warp * warps;
-                auto kern = hmk::adder_fused_kernel<8>;
+                static const int mode = getenv("HM_ADDER_MODE") ? atoi(getenv("HM_ADDER_MODE")) : 1;
+                auto kern = mode == 1 ? hmk::adder_fused_kernel<8, 1> : hmk::adder_fused_kernel<8, 0>;
                 CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 const unsigned grid = (unsigned)((n + warps - 1) / warps);
                 kern<<<grid, warps * 32, smem, ctx->stream>>>(a->d, b->d, o->d, n, a->L, make_layout(o));
@@ -1348,36 +1369,54 @@ int hm_poly_rem(hm_context *ctx, const hm_batch *a, hm_batch **out) {
     return HM_OK;
 }
 
+static bool mulrem_fresh_ok(const hm_context *ctx, const hm_batch *a, const hm_batch *b) {
+    // fused fast path: both operands fresh-shaped with D = 256, d = 128 (config A)
+    bool fresh = ctx->has_pk && ctx->fresh_deg == 256 && ctx->ds == 128 && same_layout(a, b);
+    for (uint32_t k = 0; k < a->L && fresh; ++k) fresh = a->degb[k] == 256 && b->degb[k] == 256;
+    return fresh;
+}
+
+static int mulrem_fresh_exec(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
+    const uint64_t pairs = (uint64_t)a->n * a->L;
+    if (!pairs) return HM_OK;
+    constexpr int WD = 8, WS = 4;
+    static const int mode = getenv("HM_MULREM_MODE") ? atoi(getenv("HM_MULREM_MODE")) : 2;
+    if (mode == 0) { // shift/mask schoolbook on the ALU pipe
+        constexpr int TH = 128;
+        const size_t smem = (size_t)4 * 256 * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;
+        auto kern = hmk::mulrem_fresh_kernel<WD, WS, 0, TH, 1>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid_for(ctx, pairs, TH, 6), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
+    } else if (mode == 1) { // Karatsuba on the multiplier, small CTAs, plain tables
+        constexpr int TH = 128;
+        const size_t smem = (size_t)4 * 256 * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;
+        auto kern = hmk::mulrem_fresh_kernel<WD, WS, 2, TH, 1>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid_for(ctx, pairs, TH, 4), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
+    } else { // Karatsuba on the multiplier, one 512-thread CTA per SM, 8-way replicated (conflict-free) fold tables
+        constexpr int TH = 512, REP = 8;
+        const size_t smem = (size_t)4 * 256 * REP * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;
+        auto kern = hmk::mulrem_fresh_kernel<WD, WS, 2, TH, REP>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid_for(ctx, pairs, TH, 1), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
+    }
+    return post_launch(ctx, "mulrem_fresh_kernel");
+}
+
 int hm_poly_mulrem(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out) {
     if (!ctx || !a || !b || !out) return HM_ERR_INVALID_ARGUMENT;
     if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;
     if (a->n != b->n || a->L != b->L) return HM_ERR_INVALID_ARGUMENT;
     USE_DEV(ctx);
-    // fused fast path: both operands fresh-shaped with D = 256, d = 128 (config A)
-    bool fresh = ctx->has_pk && ctx->fresh_deg == 256 && ctx->ds == 128 && same_layout(a, b);
-    for (uint32_t k = 0; k < a->L && fresh; ++k) fresh = a->degb[k] == 256 && b->degb[k] == 256;
-    if (fresh) {
+    if (mulrem_fresh_ok(ctx, a, b)) {
         std::vector<uint64_t> bounds(a->L, ctx->ds - 1);
         hm_batch *o = new_batch(ctx, a->n, a->L, bounds.data());
         if (!o) return HM_ERR_INVALID_ARGUMENT;
         int rc = alloc_batch(ctx, o);
+        if (rc == HM_OK) rc = mulrem_fresh_exec(ctx, a, b, o);
         if (rc != HM_OK) {
-            delete o;
+            hm_batch_free(ctx, o);
             return rc;
-        }
-        const uint64_t pairs = (uint64_t)a->n * a->L;
-        if (pairs) {
-            constexpr int WD = 8, WS = 4;
-            const size_t smem = (size_t)4 * 256 * WS * 4 + (size_t)2 * 2 * hmk::MR_THREADS * (WD / 2 + 1) * 8;
-            auto kern = hmk::mulrem_fresh_kernel<WD, WS>;
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = grid_for(ctx, pairs, hmk::MR_THREADS, 6);
-            kern<<<grid, hmk::MR_THREADS, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
-            rc = post_launch(ctx, "mulrem_fresh_kernel");
-            if (rc != HM_OK) {
-                hm_batch_free(ctx, o);
-                return rc;
-            }
         }
         *out = o;
         return HM_OK;
@@ -1388,6 +1427,17 @@ int hm_poly_mulrem(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_bat
     rc = hm_poly_rem(ctx, prod, out);
     hm_batch_free(ctx, prod);
     return rc;
+}
+
+int hm_poly_mulrem_into(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *out) {
+    if (!ctx || !a || !b || !out) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;
+    if (a->n != b->n || a->L != b->L || out->n != a->n || out->L != a->L) return HM_ERR_INVALID_ARGUMENT;
+    for (uint32_t k = 0; k < a->L; ++k)
+        if (out->w[k] != (uint32_t)((ctx->ds - 1) / 64 + 1)) return HM_ERR_INVALID_ARGUMENT;
+    if (!mulrem_fresh_ok(ctx, a, b)) return HM_ERR_UNSUPPORTED; // only the fused kernel writes in place
+    USE_DEV(ctx);
+    return mulrem_fresh_exec(ctx, a, b, out);
 }
 
 // ---- measured integer-logic peak ------------------------------------------------------------------
@@ -1402,7 +1452,7 @@ int hm_measure_alu_peak(hm_context *ctx, double *lop3_lane_ops_per_s, double *sm
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const int iters = 8192;
+    const int iters = 1 << 16;
     hmk::lop3_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(sink, clk, iters, 0x9e3779b9u);
     double best = 0, mhz = 0;
     for (int rep = 0; rep < 3; ++rep) {

@@ -439,17 +439,117 @@ __device__ __forceinline__ void clmul_regs(const uint32_t (&a)[NA], const uint32
 }
 
 // ----------------------------------------------------------------------------------------
+// register-resident carry-less product on the integer MULTIPLIER (FMA pipe), NA x NB 32-bit words.
+//
+// Spread trick: keep only every 4th bit of each operand word (class c = bit index mod 4).  The
+// integer product of two such words has, in every 4-bit group, the NUMBER of coefficient pairs that
+// land there (at most 8 < 16, so groups never carry into each other); its low bit is their XOR, i.e.
+// the carry-less product restricted to class (c + c') mod 4.  Products of one output class are
+// XOR-accumulated unmasked (XOR does not carry either) and masked once at the end.  A 32x32 -> 64
+// clmul is 16 IMAD.WIDE + 16 three-input LOP3, against ~48 ALU instructions for the shift/mask
+// schoolbook above — and the multiplies issue on the otherwise idle FMA pipe (tools/ubench.cu).
+// ----------------------------------------------------------------------------------------
+template <int NA, int NB>
+__device__ __forceinline__ void clmul_imad(const uint32_t (&a)[NA], const uint32_t (&b)[NB], uint32_t (&r)[NA + NB]) {
+    uint32_t as[4][NA], bs[4][NB];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int j = 0; j < NA; ++j) as[c][j] = a[j] & (0x11111111u << c);
+#pragma unroll
+        for (int k = 0; k < NB; ++k) bs[c][k] = b[k] & (0x11111111u << c);
+    }
+#pragma unroll
+    for (int i = 0; i < NA + NB; ++i) r[i] = 0;
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+        uint32_t acc[NA + NB];
+#pragma unroll
+        for (int i = 0; i < NA + NB; ++i) acc[i] = 0;
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const unsigned long long p = (unsigned long long)as[c][j] * (unsigned long long)bs[(kc - c) & 3][k];
+                    acc[j + k] ^= (uint32_t)p;
+                    acc[j + k + 1] ^= (uint32_t)(p >> 32);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NA + NB; ++i) r[i] |= acc[i] & (0x11111111u << kc);
+    }
+}
+
+// 32 x 32 -> 64 carry-less product on the multiplier (see clmul_imad): 16 IMAD.WIDE + 20 LOP3.
+__device__ __forceinline__ void clmul32_imad(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi) {
+    uint32_t as[4], bs[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        as[c] = a & (0x11111111u << c);
+        bs[c] = b & (0x11111111u << c);
+    }
+    lo = 0;
+    hi = 0;
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+        const unsigned long long p0 = (unsigned long long)as[0] * bs[kc & 3];
+        const unsigned long long p1 = (unsigned long long)as[1] * bs[(kc - 1) & 3];
+        const unsigned long long p2 = (unsigned long long)as[2] * bs[(kc - 2) & 3];
+        const unsigned long long p3 = (unsigned long long)as[3] * bs[(kc - 3) & 3];
+        const uint32_t m = 0x11111111u << kc;
+        lo |= ((uint32_t)p0 ^ (uint32_t)p1 ^ (uint32_t)p2 ^ (uint32_t)p3) & m;
+        hi |= ((uint32_t)(p0 >> 32) ^ (uint32_t)(p1 >> 32) ^ (uint32_t)(p2 >> 32) ^ (uint32_t)(p3 >> 32)) & m;
+    }
+}
+
+// Karatsuba over 32-bit words down to single-word leaves on the multiplier: N = 8 needs 27 leaf products
+// (432 IMAD.WIDE on the FMA pipe + ~900 LOP3 on the ALU pipe, the two pipes issue concurrently) instead of
+// ~3 000 ALU instructions for the shift/mask schoolbook.
+template <int N>
+__device__ __forceinline__ void clmul_kara(const uint32_t (&a)[N], const uint32_t (&b)[N], uint32_t (&r)[2 * N]) {
+    if constexpr (N == 1) {
+        clmul32_imad(a[0], b[0], r[0], r[1]);
+    } else {
+        constexpr int H = N / 2;
+        static_assert(N % 2 == 0, "power-of-two word counts only");
+        uint32_t a0[H], a1[H], b0[H], b1[H], sa[H], sb[H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            a0[i] = a[i]; a1[i] = a[H + i]; b0[i] = b[i]; b1[i] = b[H + i];
+            sa[i] = a0[i] ^ a1[i];
+            sb[i] = b0[i] ^ b1[i];
+        }
+        uint32_t p0[N], p1[N], p2[N];
+        clmul_kara<H>(a0, b0, p0);
+        clmul_kara<H>(a1, b1, p2);
+        clmul_kara<H>(sa, sb, p1);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            r[i] = p0[i];
+            r[N + i] = p2[i];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[H + i] ^= p1[i] ^ p0[i] ^ p2[i];
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // K5  remainder by the secret key S                  reference src/polynomial.rs:316-365
 //
 // d % 32 == 0: word folding, T[b][x] = (x * X^(8b) * X^d) mod S (gf2host.hpp), i.e. a CRC with
 // four 256-entry tables; WS = d/32 words of state in registers.
 // ----------------------------------------------------------------------------------------
-template <int WS>
-__device__ __forceinline__ void fold_word(uint32_t (&dst)[WS], uint32_t t, const uint32_t *__restrict__ T) {
-    const uint32_t *r0 = T + (size_t)(0 * 256 + (t & 255u)) * WS;
-    const uint32_t *r1 = T + (size_t)(1 * 256 + ((t >> 8) & 255u)) * WS;
-    const uint32_t *r2 = T + (size_t)(2 * 256 + ((t >> 16) & 255u)) * WS;
-    const uint32_t *r3 = T + (size_t)(3 * 256 + (t >> 24)) * WS;
+// REP > 1: every table row is stored REP times, copy `rep` of a row starts (rep * WS) words after copy 0, so that
+// the lanes of a quarter-warp (rep = lane % 8) read from disjoint bank groups whatever their indices are.
+template <int WS, int REP = 1>
+__device__ __forceinline__ void fold_word(uint32_t (&dst)[WS], uint32_t t, const uint32_t *__restrict__ T, uint32_t rep = 0) {
+    const uint32_t *r0 = T + ((size_t)(0 * 256 + (t & 255u)) * REP + rep) * WS;
+    const uint32_t *r1 = T + ((size_t)(1 * 256 + ((t >> 8) & 255u)) * REP + rep) * WS;
+    const uint32_t *r2 = T + ((size_t)(2 * 256 + ((t >> 16) & 255u)) * REP + rep) * WS;
+    const uint32_t *r3 = T + ((size_t)(3 * 256 + (t >> 24)) * REP + rep) * WS;
     if constexpr (WS % 4 == 0) {
 #pragma unroll
         for (int q = 0; q < WS / 4; ++q) {
@@ -527,10 +627,8 @@ __global__ void __launch_bounds__(MUL_WARPS * 32) rem_generic_kernel(View a, Vie
 //   Operand tiles are staged in shared memory by TMA (two buffers); the 2D+1-bit product stays
 //   in registers and is folded down to d bits with the tables above; only d bits are written.
 // ----------------------------------------------------------------------------------------
-constexpr int MR_THREADS = 128;
-
-template <int WD, int WS>
-__global__ void __launch_bounds__(MR_THREADS) mulrem_fresh_kernel(const uint64_t *__restrict__ A,
+template <int WD, int WS, int MODE, int MR_THREADS, int REP>
+__global__ void __launch_bounds__(MR_THREADS, MR_THREADS >= 512 ? 1 : 4) mulrem_fresh_kernel(const uint64_t *__restrict__ A,
                                                                   const uint64_t *__restrict__ B,
                                                                   uint64_t *__restrict__ O, uint64_t n,
                                                                   const uint32_t *__restrict__ Tg) {
@@ -538,10 +636,11 @@ __global__ void __launch_bounds__(MR_THREADS) mulrem_fresh_kernel(const uint64_t
     constexpr int NP = 2 * WD + 1;   // product words (bit 2D lives in the last one)
     extern __shared__ __align__(16) uint32_t smem32[];
     __shared__ __align__(8) uint64_t bars[2];
-    uint32_t *T = smem32;                                               // 4*256*WS
-    uint64_t *tiles = reinterpret_cast<uint64_t *>(smem32 + 4 * 256 * WS); // [2 bufs][2 operands][MR_THREADS*WF]
+    uint32_t *T = smem32;                                                     // 4*256*REP*WS
+    uint64_t *tiles = reinterpret_cast<uint64_t *>(smem32 + 4 * 256 * REP * WS); // [2 bufs][2 operands][MR_THREADS*WF]
     const int tid = threadIdx.x;
-    for (uint32_t i = tid; i < 4u * 256u * WS; i += MR_THREADS) T[i] = Tg[i];
+    const uint32_t rep = (REP > 1) ? (uint32_t)(tid % REP) : 0u;
+    for (uint32_t i = tid; i < 4u * 256u * REP * WS; i += MR_THREADS) T[i] = Tg[((i / WS) / REP) * WS + (i % WS)];
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -597,7 +696,9 @@ __global__ void __launch_bounds__(MR_THREADS) mulrem_fresh_kernel(const uint64_t
             }
         }
         uint32_t lowp[2 * WD];
-        clmul_regs<WD, WD>(a, b, lowp);
+        if constexpr (MODE == 0) clmul_regs<WD, WD>(a, b, lowp);
+        else if constexpr (MODE == 1) clmul_imad<WD, WD>(a, b, lowp);
+        else clmul_kara<WD>(a, b, lowp);
         uint32_t pr[NP];
 #pragma unroll
         for (int i = 0; i < 2 * WD; ++i) pr[i] = lowp[i];
@@ -611,7 +712,7 @@ __global__ void __launch_bounds__(MR_THREADS) mulrem_fresh_kernel(const uint64_t
             uint32_t dst[WS];
 #pragma unroll
             for (int q = 0; q < WS; ++q) dst[q] = pr[i - WS + q];
-            fold_word<WS>(dst, pr[i], T);
+            fold_word<WS, REP>(dst, pr[i], T, rep);
 #pragma unroll
             for (int q = 0; q < WS; ++q) pr[i - WS + q] = dst[q];
         }
@@ -646,111 +747,105 @@ template <int WD> struct AdderCfg {
     static constexpr int NP = WD + 1;      // words of p_k (bit D in the last)
     static constexpr int NG = 2 * WD + 1;  // words of g_k
     static constexpr int NM = 3 * WD + 1;  // words of m_k
-    static constexpr int TQ = 8;           // output words per tile
+    static constexpr int TQMAX = 24;       // widest output tile (words per lane per pass)
     static constexpr int PAD = NM + 7;     // zero words in front of each carry buffer (window underflow)
-    __host__ __device__ static constexpr uint32_t carry_cap(uint32_t L) { // words, multiple of TQ
-        return (((3 * (L - 1) - 1) * WD + 1 + TQ - 1) / TQ) * TQ + TQ;
+    __host__ __device__ static constexpr uint32_t carry_cap(uint32_t L) { // words
+        return (((3 * (L - 1) - 1) * WD + 1 + TQMAX - 1) / TQMAX) * TQMAX + TQMAX;
     }
     __host__ __device__ static constexpr uint32_t warp_words(uint32_t L) {
-        return L * (NP + NG + NM) + 2 * (PAD + carry_cap(L)) + 4;
+        return ((L * (NP + NG + NM) + (PAD + carry_cap(L)) + 3) / 4) * 4;
     }
 };
 
-template <int WD, int R>
-__device__ __forceinline__ void adder_step_tiles(const uint32_t *__restrict__ ccur, uint32_t *__restrict__ cnxt,
-                                                 const uint32_t *__restrict__ gk, uint32_t Bmine, uint32_t tile0,
-                                                 uint32_t ntiles, int lane) {
+// One pass of a step: lane l computes output words [w0 + l*TQ, w0 + (l+1)*TQ) of c_{k+1} = m_k*c_k + g_k.
+template <int WD, int TQ, int MODE>
+__device__ __forceinline__ void adder_step_pass(uint32_t *cbuf, const uint32_t *__restrict__ gk, uint32_t Bmine,
+                                                uint32_t w0, uint32_t len_next, int lane) {
     using C = AdderCfg<WD>;
-    constexpr int NM = C::NM, TQ = C::TQ, NW = NM + TQ; // window words per tile
-    uint32_t win[R][NW], acc[R][TQ + 1];
+    constexpr int NM = C::NM, NW = NM + TQ; // window words
+    uint32_t win[NW], acc[TQ + 1];
+    const uint32_t t0 = w0 + (uint32_t)lane * TQ;
+    const bool live = t0 < len_next;
+    {
+        // win[y] = c[t0 - NM + y]; PAD >= NM zero words sit in front of the buffer, so no lower bound check;
+        // lanes past the end of the polynomial read the (zero) front of the buffer instead
+        const uint32_t *src = cbuf + (live ? (int)t0 : 0) - NM;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const uint32_t t0 = (tile0 + lane + 32 * r) * TQ;
-        // win[y] = c[t0 - NM + y]; the buffer has PAD >= NM zero words in front, so no bounds checks
-        const uint32_t *src = ccur + (int)t0 - NM;
+        for (int y = 0; y < NW; ++y) win[y] = src[y];
 #pragma unroll
-        for (int y = 0; y < NW; ++y) win[r][y] = src[y];
-#pragma unroll
-        for (int i = 0; i <= TQ; ++i) acc[r][i] = 0;
+        for (int i = 0; i <= TQ; ++i) acc[i] = 0;
     }
+    __syncwarp(); // the carry is updated in place: every lane holds its window before anyone stores
 #pragma unroll 1
     for (int s = 31; s >= 0; --s) {
-        const uint32_t Bs = __shfl_sync(FULL, Bmine, s); // bit j set <=> bit s of m_k[j] set
+        const uint32_t Bs = __shfl_sync(FULL, Bmine, s); // bit j set <=> bit s of m_k[j] set (warp-uniform)
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int i = TQ; i > 0; --i) acc[i] = __funnelshift_l(acc[i - 1], acc[i], 1);
+        acc[0] <<= 1;
+        // acc[i] is output word t0-1+i (acc[0] = halo); it receives c[t0-1+i-j] = win[i + NM-1 - j]
+        if constexpr (MODE == 0) { // pairs of multiplier words: one 3-input LOP3 when both bits are set
 #pragma unroll
-            for (int i = TQ; i > 0; --i) acc[r][i] = __funnelshift_l(acc[r][i - 1], acc[r][i], 1);
-            acc[r][0] <<= 1;
-        }
-        // acc[i] is output word t0-1+i; it receives c[t0-1+i-j] = win[i + NM-1 - j]
+            for (int jp = 0; jp + 1 < NM; jp += 2) {
+                const uint32_t sel = (Bs >> jp) & 3u;
+                if (sel == 3u) {
 #pragma unroll
-        for (int jp = 0; jp + 1 < NM; jp += 2) {
-            const uint32_t sel = (Bs >> jp) & 3u;
-            if (sel == 3u) {
+                    for (int i = 0; i <= TQ; ++i) acc[i] ^= win[i + NM - 1 - jp] ^ win[i + NM - 2 - jp];
+                } else if (sel == 1u) {
 #pragma unroll
-                for (int r = 0; r < R; ++r)
+                    for (int i = 0; i <= TQ; ++i) acc[i] ^= win[i + NM - 1 - jp];
+                } else if (sel == 2u) {
 #pragma unroll
-                    for (int i = 0; i <= TQ; ++i) acc[r][i] ^= win[r][i + NM - 1 - jp] ^ win[r][i + NM - 2 - jp];
-            } else if (sel == 1u) {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int i = 0; i <= TQ; ++i) acc[r][i] ^= win[r][i + NM - 1 - jp];
-            } else if (sel == 2u) {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-#pragma unroll
-                    for (int i = 0; i <= TQ; ++i) acc[r][i] ^= win[r][i + NM - 2 - jp];
+                    for (int i = 0; i <= TQ; ++i) acc[i] ^= win[i + NM - 2 - jp];
+                }
             }
-        }
-        if constexpr (NM & 1) {
-            if ((Bs >> (NM - 1)) & 1u) {
+            if constexpr (NM & 1) {
+                if ((Bs >> (NM - 1)) & 1u) {
 #pragma unroll
-                for (int r = 0; r < R; ++r)
+                    for (int i = 0; i <= TQ; ++i) acc[i] ^= win[i];
+                }
+            }
+        } else { // one uniform branch per multiplier word (smaller code, fewer taken branches, more LOP3)
 #pragma unroll
-                    for (int i = 0; i <= TQ; ++i) acc[r][i] ^= win[r][i];
+            for (int j = 0; j < NM; ++j) {
+                if ((Bs >> j) & 1u) {
+#pragma unroll
+                    for (int i = 0; i <= TQ; ++i) acc[i] ^= win[i + NM - 1 - j];
+                }
             }
         }
     }
+    if (live) {
+        uint32_t o[TQ];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const uint32_t tile = tile0 + lane + 32 * r;
-        if (tile < ntiles) {
-            const uint32_t t0 = tile * TQ;
-            uint32_t o[TQ];
-#pragma unroll
-            for (int i = 0; i < TQ; ++i) {
-                const uint32_t x = t0 + i;
-                o[i] = acc[r][i + 1] ^ ((x < (uint32_t)C::NG) ? gk[x] : 0u);
-            }
-            uint4 *dst = reinterpret_cast<uint4 *>(cnxt + t0);
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        for (int i = 0; i < TQ; ++i) {
+            const uint32_t x = t0 + i;
+            o[i] = acc[i + 1] ^ ((x < (uint32_t)C::NG) ? gk[x] : 0u);
         }
+        uint4 *dst = reinterpret_cast<uint4 *>(cbuf + t0);
+#pragma unroll
+        for (int q = 0; q < TQ / 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
     }
 }
 
-template <int WD>
-__global__ void __launch_bounds__(128) adder_fused_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
-                                                          uint64_t *__restrict__ O, uint64_t n, uint32_t L, Layout lo) {
+template <int WD, int MODE>
+__global__ void __launch_bounds__(128, 5) adder_fused_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
+                                                             uint64_t *__restrict__ O, uint64_t n, uint32_t L, Layout lo) {
     using C = AdderCfg<WD>;
     constexpr int WF = WD / 2 + 1;
-    constexpr int NP = C::NP, NG = C::NG, NM = C::NM, TQ = C::TQ;
+    constexpr int NP = C::NP, NG = C::NG, NM = C::NM;
     extern __shared__ __align__(16) uint32_t smem32[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t v = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (v >= n) return;
     const uint32_t cap = C::carry_cap(L);
     uint32_t *base = smem32 + (size_t)warp * C::warp_words(L);
-    // carry buffers first (16-byte aligned: warp_words is a multiple of 4, PAD+cap multiple of ... see static_assert)
-    uint32_t *cbuf0 = base;                       // PAD zeros + cap words
-    uint32_t *cbuf1 = base + (C::PAD + cap);
-    uint32_t *P = base + 2 * (C::PAD + cap);      // L x NP
+    uint32_t *cb = base + C::PAD;                 // carry c_k: PAD zero words in front, cap words (16-byte aligned)
+    uint32_t *P = base + (C::PAD + cap);          // L x NP
     uint32_t *G = P + L * NP;                     // L x NG
     uint32_t *M = G + L * NG;                     // L x NM
-    static_assert((C::PAD % 4) == 0, "carry buffers must stay 16-byte aligned");
+    static_assert((C::PAD % 4) == 0 && (C::TQMAX % 4) == 0, "carry buffers must stay 16-byte aligned");
 
-    for (uint32_t i = lane; i < 2 * (C::PAD + cap); i += 32) base[i] = 0;
+    for (uint32_t i = lane; i < C::PAD + cap; i += 32) base[i] = 0;
 
     // ---- stage 1: per-bit products, lane k owns bit k ------------------------------------
     const uint64_t *Av = A + v * (uint64_t)L * WF, *Bv = B + v * (uint64_t)L * WF;
@@ -807,8 +902,7 @@ __global__ void __launch_bounds__(128) adder_fused_kernel(const uint64_t *__rest
         const uint32_t x0 = (2 * j < (uint32_t)NP) ? P[2 * j] : 0u, x1 = (2 * j + 1 < (uint32_t)NP) ? P[2 * j + 1] : 0u;
         Ov[lo.off[0] + j] = (uint64_t)x0 | ((uint64_t)x1 << 32);
     }
-    uint32_t *ccur = cbuf0 + C::PAD, *cnxt = cbuf1 + C::PAD;
-    for (uint32_t j = lane; j < (uint32_t)NG; j += 32) ccur[j] = G[j];
+    for (uint32_t j = lane; j < (uint32_t)NG; j += 32) cb[j] = G[j];
     __syncwarp();
 
     // ---- serial chain ---------------------------------------------------------------------
@@ -819,7 +913,7 @@ __global__ void __launch_bounds__(128) adder_fused_kernel(const uint64_t *__rest
             uint64_t *dst = Ov + lo.off[k];
             const uint32_t *pk = P + k * NP;
             for (uint32_t j = lane; j < wo; j += 32) {
-                uint32_t x0 = ccur[2 * j], x1 = ccur[2 * j + 1];
+                uint32_t x0 = cb[2 * j], x1 = cb[2 * j + 1];
                 if (2 * j < (uint32_t)NP) x0 ^= pk[2 * j];
                 if (2 * j + 1 < (uint32_t)NP) x1 ^= pk[2 * j + 1];
                 dst[j] = (uint64_t)x0 | ((uint64_t)x1 << 32);
@@ -833,25 +927,24 @@ __global__ void __launch_bounds__(128) adder_fused_kernel(const uint64_t *__rest
 #pragma unroll
             for (int j = 0; j < NM; ++j) Bmine |= ((mk[j] >> lane) & 1u) << j;
         }
-        const uint32_t len_next = (3 * k + 2) * WD + 1;       // words of c_{k+1}
-        const uint32_t ntiles = (len_next + TQ - 1) / TQ;
+        const uint32_t len_next = (3 * k + 2) * WD + 1; // words of c_{k+1}
         const uint32_t *gk = G + k * NG;
-        uint32_t tile0 = 0;
-        while (tile0 < ntiles) {
-            const uint32_t left = ntiles - tile0;
-            if (left > 64) {
-                adder_step_tiles<WD, 3>(ccur, cnxt, gk, Bmine, tile0, ntiles, lane);
-                tile0 += 96;
-            } else if (left > 32) {
-                adder_step_tiles<WD, 2>(ccur, cnxt, gk, Bmine, tile0, ntiles, lane);
-                tile0 += 64;
-            } else {
-                adder_step_tiles<WD, 1>(ccur, cnxt, gk, Bmine, tile0, ntiles, lane);
-                tile0 += 32;
-            }
+        __syncwarp(); // s_k has been read out of the buffer
+        // passes of 32 lanes x TQ words, highest words first: a pass only reads words below its own top, so the
+        // in-place update never clobbers what a later (lower) pass still needs
+        constexpr uint32_t FULLW = 32 * 24;
+        const uint32_t nfull = (len_next - 1) / FULLW;
+        {
+            const uint32_t w0 = nfull * FULLW, left = len_next - w0;
+            if (left > 32 * 16) adder_step_pass<WD, 24, MODE>(cb, gk, Bmine, w0, len_next, lane);
+            else if (left > 32 * 8) adder_step_pass<WD, 16, MODE>(cb, gk, Bmine, w0, len_next, lane);
+            else adder_step_pass<WD, 8, MODE>(cb, gk, Bmine, w0, len_next, lane);
+        }
+        for (uint32_t f = nfull; f-- > 0;) {
+            __syncwarp();
+            adder_step_pass<WD, 24, MODE>(cb, gk, Bmine, f * FULLW, len_next, lane);
         }
         __syncwarp();
-        uint32_t *tsw = ccur; ccur = cnxt; cnxt = tsw;
     }
 }
 

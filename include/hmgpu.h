@@ -134,6 +134,9 @@ int hm_batch_clone(hm_context *ctx, const hm_batch *b, hm_batch **out);
 int hm_encrypt(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, const uint8_t *masks, hm_batch **out);
 int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
                       hm_batch **out);
+/* Same, writing into an existing batch of n values x L fresh-width slots (no allocation). */
+int hm_encrypt_device_into(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
+                           hm_batch *out);
 /* Context::decrypt -> Ciphered::try_decipher -> CipheredBit::decipher — src/context.rs:480-488,
  * src/cipher.rs:217-250, :119-122.  Writes n * (L/8) bytes.  L % 8 != 0 -> HM_ERR_INVALID_LENGTH. */
 int hm_decrypt(hm_context *ctx, const hm_batch *b, uint8_t *values_out);
@@ -176,6 +179,9 @@ int hm_poly_add(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch 
 int hm_poly_mul(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out);
 int hm_poly_rem(hm_context *ctx, const hm_batch *a, hm_batch **out);
 int hm_poly_mulrem(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out);
+/* Fused mul+rem into an existing result batch (fresh operands at a tuned parameter set only; else
+ * HM_ERR_UNSUPPORTED). */
+int hm_poly_mulrem_into(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *out);
 
 /* ---- Measurement support ---------------------------------------------------------------------
  * Runs a LOP3 issue-rate probe on the context's device and reports 32-bit LOP3 lane-operations per
