@@ -304,7 +304,7 @@ def run_ours(args, rank, local_rank, world):
         # decrypt after add (HBM bound: 46 912 B per value)
         dout = torch.empty(n * 4, dtype=torch.uint8, device=f"cuda:{local_rank}")
         s = timed(lambda: lib.hm_decrypt_device(ctx._h, out._h, dout.data_ptr()))
-        extra["decrypt_after_add"] = {"value": n / s, "unit": "u32/s", "kernel": "decrypt_slots_kernel", "ms": s * 1e3,
+        extra["decrypt_after_add"] = {"value": n / s, "unit": "u32/s", "kernel": "decrypt_value_tma_kernel<2,256> x 2 CTAs/SM", "ms": s * 1e3,
                                       "hbm_GBps": n * 46912 / s / 1e9, "hbm_frac": n * 46912 / s / 1e9 / hbm_peak}
         s = timed(lambda: lib.hm_decrypt_device(ctx._h, ca._h, dout.data_ptr()), reps=20)
         extra["decrypt_fresh"] = {"value": n / s, "unit": "u32/s", "kernel": "decrypt_uniform_kernel", "ms": s * 1e3,

@@ -784,6 +784,32 @@ int hm_decrypt_device(hm_context *ctx, const hm_batch *b, uint8_t *d_values_out)
         const int grid = grid_for(ctx, units, hmk::DEC_THREADS, per_sm);
         hmk::decrypt_uniform_kernel<<<grid, hmk::DEC_THREADS, smem, ctx->stream>>>(b->d, ctx->d_v, d_values_out, units, w);
         LAUNCHED("decrypt_uniform_kernel");
+    } else if (!getenv("HM_DECRYPT_NO_TMA") && (b->value_words * 8) % 16 == 0 && b->value_words * 8 * 2 + 4096 <= ctx->smem_optin - 2048 &&
+               b->value_words >= 256 && ((uintptr_t)b->d % 16) == 0) {
+        // whole values streamed through shared memory by TMA (adder / multiplier results)
+        uint32_t wmax = 0;
+        for (uint32_t k = 0; k < b->L; ++k) wmax = std::max(wmax, b->w[k]);
+        int rc = ensure_decrypt_vector(ctx, (size_t)wmax * 64);
+        if (rc != HM_OK) return rc;
+        const size_t vbytes = b->value_words * 8, extra = (size_t)wmax * 8 + 16;
+        const size_t budget = ctx->smem_optin - 2048;
+        static const int decv = getenv("HM_DECV") ? atoi(getenv("HM_DECV")) : 1;
+#define DECV_LAUNCH(ST, TH, PER_SM)                                                                                   \
+    {                                                                                                                 \
+        auto kern = hmk::decrypt_value_tma_kernel<ST, TH>;                                                            \
+        const size_t smem = vbytes * ST + extra;                                                                      \
+        const int grid = (int)std::min<uint64_t>(b->n, (uint64_t)ctx->sm_count * PER_SM);                             \
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+        kern<<<grid, TH, smem, ctx->stream>>>(b->d, ctx->d_v, wmax, d_values_out, b->n, make_layout(b));              \
+    }
+        if (decv == 1 && 4 * (vbytes * 4 + extra + 1024) <= budget) DECV_LAUNCH(4, 256, 4)
+        else if (decv == 1 && 2 * (vbytes * 2 + extra + 1024) <= budget) DECV_LAUNCH(2, 256, 2)
+        else if (decv == 2 && 4 * (vbytes * 1 + extra + 1024) <= budget) DECV_LAUNCH(1, 128, 4)
+        else if (vbytes * 4 + extra <= budget) DECV_LAUNCH(4, 512, 1)
+        else if (vbytes * 3 + extra <= budget) DECV_LAUNCH(3, 512, 1)
+        else DECV_LAUNCH(2, 512, 1)
+#undef DECV_LAUNCH
+        LAUNCHED("decrypt_value_tma_kernel");
     } else {
         int rc = ensure_vv(ctx, b);
         if (rc != HM_OK) return rc;

@@ -67,6 +67,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// global -> shared in pieces of at most `piece` bytes, all completing on `bar` (several bulk requests in flight
+// instead of one long one).  Caller has already armed `bar` with the total byte count.
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar);
+__device__ __forceinline__ void tma_load_1d_pieces(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar,
+                                                   uint32_t piece) {
+    for (uint32_t o = 0; o < bytes; o += piece)
+        tma_load_1d(static_cast<char *>(smem_dst) + o, static_cast<const char *>(gsrc) + o,
+                    (bytes - o < piece) ? (bytes - o) : piece, bar);
+}
 // global -> shared, completion counted in bytes on `bar`.  16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -301,6 +310,67 @@ __global__ void __launch_bounds__(256) decrypt_slots_kernel(const uint64_t *__re
     }
     __syncthreads();
     if (threadIdx.x == 0 && (uint64_t)blockIdx.x * 8 < units) out[blockIdx.x] = (uint8_t)bits;
+}
+
+// Ragged layouts whose whole value fits in shared memory a few times over (results of the adder: 46.9 KB per
+// u32): one persistent 512-thread CTA per SM streams whole values through a STAGES-deep ring of TMA bulk loads
+// (the copy engine keeps (STAGES-1) x value_bytes in flight per SM, no thread waits on a global load), the
+// decrypt vector v sits in shared memory, warp w reduces slots w, w+16, ... and the L plaintext bits are
+// assembled in shared memory.
+template <int STAGES, int DECV_THREADS>
+__global__ void __launch_bounds__(DECV_THREADS) decrypt_value_tma_kernel(const uint64_t *__restrict__ ct,
+                                                                           const uint64_t *__restrict__ v, uint32_t vwords,
+                                                                           uint8_t *__restrict__ out, uint64_t n, Layout lay) {
+    extern __shared__ __align__(16) uint64_t smem64[];
+    __shared__ __align__(8) uint64_t bars[STAGES];
+    __shared__ uint32_t sbits[2][MAX_SLOTS / 32];
+    const uint32_t VW = lay.value_words;
+    uint64_t *bufs = smem64;                        // STAGES x VW words (VW*8 is a multiple of 16)
+    uint64_t *sv = smem64 + (size_t)STAGES * VW;    // decrypt vector, vwords = widest slot
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < vwords; i += DECV_THREADS) sv[i] = v[i];
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+    const uint64_t mine = (n > first) ? (n - first + stride - 1) / stride : 0;
+    const uint32_t vbytes = VW * 8;
+    if (tid == 0)
+        for (uint32_t j = 0; j + 1 < (uint32_t)STAGES && j < mine; ++j) {
+            mbar_expect_tx(&bars[j], vbytes);
+            tma_load_1d(bufs + (size_t)j * VW, ct + (first + j * stride) * VW, vbytes, &bars[j]);
+        }
+    const uint32_t nbytes = lay.L / 8;
+    for (uint64_t i = 0; i < mine; ++i) {
+        const uint32_t st = (uint32_t)(i % STAGES);
+        const uint64_t ahead = i + STAGES - 1;
+        if (tid == 0 && ahead < mine) { // refill the buffer consumed in the previous iteration
+            const uint32_t sa = (uint32_t)(ahead % STAGES);
+            mbar_expect_tx(&bars[sa], vbytes);
+            tma_load_1d(bufs + (size_t)sa * VW, ct + (first + ahead * stride) * VW, vbytes, &bars[sa]);
+        }
+        uint32_t *bits = sbits[i & 1];
+        if (tid < MAX_SLOTS / 32) bits[tid] = 0;
+        __syncthreads();
+        mbar_wait(&bars[st], (uint32_t)((i / STAGES) & 1));
+        const uint64_t *c = bufs + (size_t)st * VW;
+        for (uint32_t k = warp; k < lay.L; k += DECV_THREADS / 32) {
+            const uint32_t o = lay.off[k], w = lay.off[k + 1] - o;
+            uint64_t acc = 0;
+            for (uint32_t j = lane; j < w; j += 32) acc ^= c[o + j] & sv[j];
+            uint32_t par = __popcll(acc) & 1u;
+            par ^= __shfl_xor_sync(FULL, par, 16);
+            par ^= __shfl_xor_sync(FULL, par, 8);
+            par ^= __shfl_xor_sync(FULL, par, 4);
+            par ^= __shfl_xor_sync(FULL, par, 2);
+            par ^= __shfl_xor_sync(FULL, par, 1);
+            if (lane == 0 && par) atomicOr(&bits[k >> 5], 1u << (k & 31));
+        }
+        __syncthreads();
+        if ((uint32_t)tid < nbytes) out[(first + i * stride) * nbytes + tid] = (uint8_t)(bits[tid >> 2] >> (8 * (tid & 3)));
+    }
 }
 
 // ----------------------------------------------------------------------------------------
