@@ -30,7 +30,7 @@ HM_OP_AND, HM_OP_OR, HM_OP_XOR, HM_OP_NOT, HM_OP_ADD, HM_OP_MUL = range(6)
 
 def build(force: bool = False) -> str:
     """Compile csrc/ into libhmgpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("hmgpu.cu", "kernels.cuh", "gf2host.hpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("hmgpu.cu", "kernels_b.cu", "kernels.cuh", "gf2host.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "hmgpu.h"))
     stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
     if force or stale:
@@ -83,6 +83,10 @@ def lib() -> C.CDLL:
         "hm_batch_upload_bounded": (C.c_int, [vp, sz, C.c_uint32, u64p, vp, C.POINTER(vp)]),
         "hm_batch_download": (C.c_int, [vp, vp, vp]),
         "hm_batch_clone": (C.c_int, [vp, vp, C.POINTER(vp)]),
+        "hm_batch_serialized_size": (sz, [vp]),
+        "hm_batch_serialize": (C.c_int, [vp, vp, vp, sz]),
+        "hm_batch_deserialize": (C.c_int, [vp, vp, sz, C.POINTER(vp)]),
+        "hm_batch_download_canonical": (C.c_int, [vp, vp, vp, sz, C.POINTER(sz)]),
         "hm_host_alloc": (vp, [sz]),
         "hm_host_free": (None, [vp]),
         "hm_encrypt": (C.c_int, [vp, vp, sz, C.c_uint32, vp, C.POINTER(vp)]),

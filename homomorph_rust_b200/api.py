@@ -273,6 +273,37 @@ class Ciphered:
         off = int(w[:k].sum())
         return host[:, off : off + int(w[k])]
 
+    def to_bytes(self) -> bytes:
+        """Engine wire format (include/hmgpu.h); the reference has no ciphertext serialisation."""
+        size = N.lib().hm_batch_serialized_size(self._h)
+        buf = np.zeros(size, dtype=np.uint8)
+        _check(self._ctx._h, N.lib().hm_batch_serialize(self._ctx._h, self._h, buf.ctypes.data, size))
+        return buf.tobytes()
+
+    @classmethod
+    def from_bytes(cls, ctx: "Context", data: bytes) -> "Ciphered":
+        arr = np.frombuffer(data, dtype=np.uint8)
+        out = C.c_void_p()
+        rc = N.lib().hm_batch_deserialize(ctx._h, arr.ctypes.data, arr.size, C.byref(out))
+        if rc == N.HM_ERR_INVALID_PARAMETERS:
+            raise ValueError("batch was written under different parameters")
+        _check(ctx._h, rc)
+        return cls(ctx, out.value)
+
+    def canonical(self):
+        """[(degree, words)] per polynomial, value-major then slot-minor: the reference's Polynomial state."""
+        cnt = C.c_size_t(0)
+        _check(self._ctx._h, N.lib().hm_batch_download_canonical(self._ctx._h, self._h, None, 0, C.byref(cnt)))
+        buf = np.zeros(cnt.value, dtype=np.uint64)
+        _check(self._ctx._h, N.lib().hm_batch_download_canonical(self._ctx._h, self._h, buf.ctypes.data, buf.size, C.byref(cnt)))
+        out, pos = [], 0
+        while pos < cnt.value:
+            deg = int(buf[pos])
+            nw = deg // 64 + 1
+            out.append((deg, buf[pos + 1 : pos + 1 + nw].copy()))
+            pos += 1 + nw
+        return out
+
     def clone(self) -> "Ciphered":
         out = C.c_void_p()
         _check(self._ctx._h, N.lib().hm_batch_clone(self._ctx._h, self._h, C.byref(out)))

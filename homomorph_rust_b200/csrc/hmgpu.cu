@@ -21,6 +21,11 @@
 #include "gf2host.hpp"
 #include "kernels.cuh"
 
+namespace hmk {
+cudaError_t launch_mulrem_fresh_b(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
+                                  int sm_count, cudaStream_t stream); // kernels_b.cu
+}
+
 using hmk::Layout;
 using hmk::MulOp;
 using hmk::View;
@@ -644,6 +649,122 @@ int hm_batch_clone(hm_context *ctx, const hm_batch *b, hm_batch **out) {
     }
     if (b->n) CK(cudaMemcpyAsync(c->d, b->d, b->n * b->value_words * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     *out = c;
+    return HM_OK;
+}
+
+// ---- wire format ------------------------------------------------------------------------------------
+// The reference has no ciphertext serialisation (CipheredBit's field is private, src/cipher.rs:30); this is the
+// engine's own, little endian:
+//   "HMB1" | u16 d, dp, delta, tau | u32 L | u64 n | L x u64 degree bound | n * value_words x u64 (padded layout)
+namespace {
+struct WireHeader {
+    char magic[4];
+    uint16_t d, dp, delta, tau;
+    uint32_t L;
+    uint64_t n;
+};
+constexpr size_t WIRE_HEADER_BYTES = 4 + 8 + 4 + 8;
+void put(uint8_t *&p, const void *src, size_t n) {
+    memcpy(p, src, n);
+    p += n;
+}
+void get(const uint8_t *&p, void *dst, size_t n) {
+    memcpy(dst, p, n);
+    p += n;
+}
+} // namespace
+
+size_t hm_batch_serialized_size(const hm_batch *b) {
+    if (!b) return 0;
+    return WIRE_HEADER_BYTES + (size_t)b->L * 8 + b->n * b->value_words * 8;
+}
+
+int hm_batch_serialize(hm_context *ctx, const hm_batch *b, uint8_t *out, size_t capacity) {
+    if (!ctx || !b || !out) return HM_ERR_INVALID_ARGUMENT;
+    if (capacity < hm_batch_serialized_size(b)) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    uint8_t *p = out;
+    put(p, "HMB1", 4);
+    put(p, &ctx->d, 2);
+    put(p, &ctx->dp, 2);
+    put(p, &ctx->delta, 2);
+    put(p, &ctx->tau, 2);
+    put(p, &b->L, 4);
+    const uint64_t n = b->n;
+    put(p, &n, 8);
+    put(p, b->degb.data(), (size_t)b->L * 8);
+    if (b->n) CK(cudaMemcpyAsync(p, b->d, b->n * b->value_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HM_OK;
+}
+
+int hm_batch_deserialize(hm_context *ctx, const uint8_t *in, size_t len, hm_batch **out) {
+    if (!ctx || !in || !out) return HM_ERR_INVALID_ARGUMENT;
+    if (len < WIRE_HEADER_BYTES || memcmp(in, "HMB1", 4) != 0) return HM_ERR_INVALID_ARGUMENT;
+    const uint8_t *p = in + 4;
+    uint16_t d, dp, delta, tau;
+    uint32_t L;
+    uint64_t n;
+    get(p, &d, 2);
+    get(p, &dp, 2);
+    get(p, &delta, 2);
+    get(p, &tau, 2);
+    get(p, &L, 4);
+    get(p, &n, 8);
+    if (d != ctx->d || dp != ctx->dp || delta != ctx->delta || tau != ctx->tau) return HM_ERR_INVALID_PARAMETERS;
+    if (L == 0 || L > (uint32_t)hmk::MAX_SLOTS || len < WIRE_HEADER_BYTES + (size_t)L * 8) return HM_ERR_INVALID_ARGUMENT;
+    std::vector<uint64_t> degb(L);
+    get(p, degb.data(), (size_t)L * 8);
+    size_t vw = 0;
+    for (uint32_t k = 0; k < L; ++k) {
+        if (degb[k] > ((uint64_t)1 << 40)) return HM_ERR_INVALID_ARGUMENT;
+        vw += degb[k] / 64 + 1;
+    }
+    if (len != WIRE_HEADER_BYTES + (size_t)L * 8 + n * vw * 8) return HM_ERR_INVALID_LENGTH;
+    // the body may be unaligned inside the caller's buffer: upload byte-wise
+    USE_DEV(ctx);
+    hm_batch *b = new_batch(ctx, n, L, degb.data());
+    if (!b) return HM_ERR_INVALID_ARGUMENT;
+    int rc = alloc_batch(ctx, b);
+    if (rc != HM_OK) {
+        delete b;
+        return rc;
+    }
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(b->d, p, n * vw * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            hm_batch_free(ctx, b);
+            return fail_cuda(ctx, e, "deserialize upload");
+        }
+    }
+    *out = b;
+    return HM_OK;
+}
+
+// Canonical export: for every polynomial (value-major, slot-minor) `u64 degree` then degree/64+1 words — exactly the
+// (degree, coefficients) pair the reference's Polynomial holds (src/polynomial.rs:22-26, :404-426).  Returns the
+// number of u64 written in *written; with out == NULL only counts.
+int hm_batch_download_canonical(hm_context *ctx, const hm_batch *b, uint64_t *out, size_t capacity_words, size_t *written) {
+    if (!ctx || !b || !written) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    std::vector<uint64_t> host(b->n * b->value_words);
+    if (b->n) CK(cudaMemcpyAsync(host.data(), b->d, host.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t pos = 0;
+    for (size_t v = 0; v < b->n; ++v)
+        for (uint32_t k = 0; k < b->L; ++k) {
+            const uint64_t *w = &host[v * b->value_words + b->off[k]];
+            const size_t deg = gf2::degree(w, b->w[k]);
+            const size_t nw = deg / 64 + 1;
+            if (out) {
+                if (pos + 1 + nw > capacity_words) return HM_ERR_INVALID_ARGUMENT;
+                out[pos] = deg;
+                memcpy(out + pos + 1, w, nw * 8);
+            }
+            pos += 1 + nw;
+        }
+    *written = pos;
     return HM_OK;
 }
 
@@ -1396,15 +1517,21 @@ int hm_poly_rem(hm_context *ctx, const hm_batch *a, hm_batch **out) {
 }
 
 static bool mulrem_fresh_ok(const hm_context *ctx, const hm_batch *a, const hm_batch *b) {
-    // fused fast path: both operands fresh-shaped with D = 256, d = 128 (config A)
-    bool fresh = ctx->has_pk && ctx->fresh_deg == 256 && ctx->ds == 128 && same_layout(a, b);
-    for (uint32_t k = 0; k < a->L && fresh; ++k) fresh = a->degb[k] == 256 && b->degb[k] == 256;
+    // fused fast path: both operands fresh-shaped with (D, d) = (256, 128) [config A] or (1024, 512) [config B]
+    const bool cfg_a = ctx->fresh_deg == 256 && ctx->ds == 128, cfg_b = ctx->fresh_deg == 1024 && ctx->ds == 512;
+    bool fresh = ctx->has_pk && (cfg_a || cfg_b) && same_layout(a, b);
+    for (uint32_t k = 0; k < a->L && fresh; ++k) fresh = a->degb[k] == ctx->fresh_deg && b->degb[k] == ctx->fresh_deg;
     return fresh;
 }
 
 static int mulrem_fresh_exec(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
     const uint64_t pairs = (uint64_t)a->n * a->L;
     if (!pairs) return HM_OK;
+    if (ctx->fresh_deg == 1024) {
+        CK(hmk::launch_mulrem_fresh_b(a->d, b->d, o->d, pairs, ctx->d_remT, ctx->sm_count, ctx->stream));
+        ctx->launches++;
+        return HM_OK;
+    }
     constexpr int WD = 8, WS = 4;
     static const int mode = getenv("HM_MULREM_MODE") ? atoi(getenv("HM_MULREM_MODE")) : 2;
     if (mode == 0) { // shift/mask schoolbook on the ALU pipe

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encrypt_tab_kernel(EncParams p
 }
 
 // Generic path: any tau / D / window, table read from shared memory if it fits, else from L2.
-__global__ void __launch_bounds__(256) encrypt_generic_kernel(EncParams p) {
+static __global__ void __launch_bounds__(256) encrypt_generic_kernel(EncParams p) {
     extern __shared__ __align__(16) uint64_t smem64[];
     const uint64_t *tab = p.table;
     if (p.table_in_smem) {
@@ -223,7 +223,7 @@ constexpr int DEC_THREADS = 256;
 // Uniform slot width w (fresh ciphertexts): tiles of 256 slots staged in shared memory by TMA,
 // double buffered; thread per slot; result bits packed by ballot (bit k of the value is slot k,
 // src/cipher.rs:227-237, so 32 consecutive slots are 4 consecutive output bytes).
-__global__ void __launch_bounds__(DEC_THREADS) decrypt_uniform_kernel(const uint64_t *__restrict__ ct,
+static __global__ void __launch_bounds__(DEC_THREADS) decrypt_uniform_kernel(const uint64_t *__restrict__ ct,
                                                                       const uint64_t *__restrict__ v,
                                                                       uint8_t *__restrict__ out, uint64_t units,
                                                                       uint32_t w) {
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decrypt_uniform_kernel(const uint
 
 // Any slot layout: one warp per slot, lanes stride the slot's words (coalesced), shuffle parity.
 // vv is v laid out like one value: vv[off[k] + j] = v[j].
-__global__ void __launch_bounds__(256) decrypt_slots_kernel(const uint64_t *__restrict__ ct,
+static __global__ void __launch_bounds__(256) decrypt_slots_kernel(const uint64_t *__restrict__ ct,
                                                             const uint64_t *__restrict__ vv,
                                                             uint8_t *__restrict__ out, uint64_t units, Layout lay) {
     __shared__ uint32_t bits;
@@ -376,20 +376,20 @@ __global__ void __launch_bounds__(DECV_THREADS) decrypt_value_tma_kernel(const u
 // ----------------------------------------------------------------------------------------
 // K1  XOR / NOT                                     reference src/polynomial.rs:190-243
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) xor_flat_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b,
+static __global__ void __launch_bounds__(256) xor_flat_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b,
                                                        uint4 *__restrict__ o, uint64_t n16) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 x = __ldg(a + i), y = __ldg(b + i);
         o[i] = make_uint4(x.x ^ y.x, x.y ^ y.y, x.z ^ y.z, x.w ^ y.w);
     }
 }
-__global__ void __launch_bounds__(256) xor_flat_tail_kernel(const uint64_t *a, const uint64_t *b, uint64_t *o,
+static __global__ void __launch_bounds__(256) xor_flat_tail_kernel(const uint64_t *a, const uint64_t *b, uint64_t *o,
                                                             uint64_t from, uint64_t to) {
     const uint64_t i = from + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < to) o[i] = a[i] ^ b[i];
 }
 // Different layouts: out slot k = a slot k XOR b slot k, each zero-extended to the output width.
-__global__ void __launch_bounds__(256) xor_layout_kernel(const uint64_t *__restrict__ a, Layout la,
+static __global__ void __launch_bounds__(256) xor_layout_kernel(const uint64_t *__restrict__ a, Layout la,
                                                          const uint64_t *__restrict__ b, Layout lb,
                                                          uint64_t *__restrict__ o, Layout lo, uint64_t n) {
     const uint64_t total = n * lo.value_words;
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(256) xor_layout_kernel(const uint64_t *__restr
     }
 }
 // gate_not: a + 1, flips the constant term of every slot (common.rs:29-35).
-__global__ void __launch_bounds__(256) not_kernel(uint64_t *d, Layout lay, uint64_t n) {
+static __global__ void __launch_bounds__(256) not_kernel(uint64_t *d, Layout lay, uint64_t n) {
     const uint64_t total = n * lay.L;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t v = i / lay.L;
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256) not_kernel(uint64_t *d, Layout lay, uint6
 }
 // o[v][0..o.w) = (zero-extended) a[v] XOR b[v];  b.base may be null (copy / widen).  In place allowed
 // when o aliases a or b slot-for-slot.
-__global__ void __launch_bounds__(256) xor_views_kernel(View o, View a, View b, uint64_t n) {
+static __global__ void __launch_bounds__(256) xor_views_kernel(View o, View a, View b, uint64_t n) {
     const uint64_t total = n * o.w;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t v = i / o.w;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(256) xor_views_kernel(View o, View a, View b, 
 // ----------------------------------------------------------------------------------------
 constexpr int MUL_WARPS = 4;
 
-__global__ void __launch_bounds__(MUL_WARPS * 32) mul_views_kernel(const MulOp *__restrict__ ops, uint64_t n,
+static __global__ void __launch_bounds__(MUL_WARPS * 32) mul_views_kernel(const MulOp *__restrict__ ops, uint64_t n,
                                                                    uint32_t smem_words_per_warp) {
     extern __shared__ __align__(16) uint32_t smem32[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(128) rem_fold_kernel(View a, View o, uint64_t 
 }
 
 // Any d >= 1: warp-cooperative long division in shared memory (slow; small/odd parameter sets only).
-__global__ void __launch_bounds__(MUL_WARPS * 32) rem_generic_kernel(View a, View o, uint64_t n,
+static __global__ void __launch_bounds__(MUL_WARPS * 32) rem_generic_kernel(View a, View o, uint64_t n,
                                                                      const uint32_t *__restrict__ Sg, uint32_t d,
                                                                      uint32_t smem_words_per_warp) {
     extern __shared__ __align__(16) uint32_t smem32[];
@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(MUL_WARPS * 32) rem_generic_kernel(View a, Vie
 //   in registers and is folded down to d bits with the tables above; only d bits are written.
 // ----------------------------------------------------------------------------------------
 template <int WD, int WS, int MODE, int MR_THREADS, int REP>
-__global__ void __launch_bounds__(MR_THREADS, MR_THREADS >= 512 ? 1 : 4) mulrem_fresh_kernel(const uint64_t *__restrict__ A,
+__global__ void __launch_bounds__(MR_THREADS, WD >= 32 ? 2 : (MR_THREADS >= 512 ? 1 : 4)) mulrem_fresh_kernel(const uint64_t *__restrict__ A,
                                                                   const uint64_t *__restrict__ B,
                                                                   uint64_t *__restrict__ O, uint64_t n,
                                                                   const uint32_t *__restrict__ Tg) {
@@ -1023,7 +1023,7 @@ __global__ void __launch_bounds__(128, 5) adder_fused_kernel(const uint64_t *__r
 // 8 independent dependency chains per thread, 8 warps per CTA, 8 CTAs per SM.
 // ----------------------------------------------------------------------------------------
 constexpr int PEAK_ILP = 8;
-__global__ void __launch_bounds__(256) lop3_peak_kernel(uint32_t *sink, unsigned long long *clk, int iters, uint32_t seed) {
+static __global__ void __launch_bounds__(256) lop3_peak_kernel(uint32_t *sink, unsigned long long *clk, int iters, uint32_t seed) {
     uint32_t x[PEAK_ILP], y[PEAK_ILP];
 #pragma unroll
     for (int i = 0; i < PEAK_ILP; ++i) {

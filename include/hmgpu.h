@@ -115,6 +115,18 @@ int hm_batch_upload_bounded(hm_context *ctx, size_t n, uint32_t L, const uint64_
                             const uint64_t *host, hm_batch **out);
 /* Copies the L per-slot degree bounds the engine tracks for this batch. */
 int hm_batch_slot_degree_bounds(const hm_batch *b, uint64_t *bounds_out);
+/* ---- Wire format (engine-defined: the reference has no ciphertext serialisation, src/cipher.rs:30) ----
+ * little endian: "HMB1" | u16 d, dp, delta, tau | u32 L | u64 n | L x u64 degree bound |
+ *                n * value_words x u64 coefficient words (padded layout above).
+ * deserialize rejects a buffer written under other parameters with HM_ERR_INVALID_PARAMETERS. */
+size_t hm_batch_serialized_size(const hm_batch *b);
+int hm_batch_serialize(hm_context *ctx, const hm_batch *b, uint8_t *out, size_t capacity);
+int hm_batch_deserialize(hm_context *ctx, const uint8_t *in, size_t len, hm_batch **out);
+/* Canonical export for offline comparison with a Rust build of the reference: per polynomial (value-major,
+ * slot-minor) `u64 degree` followed by degree/64+1 words — what Polynomial holds (src/polynomial.rs:22-26).
+ * out may be NULL to only count; *written = number of u64. */
+int hm_batch_download_canonical(hm_context *ctx, const hm_batch *b, uint64_t *out, size_t capacity_words,
+                                size_t *written);
 /* Page-locked host memory for the host-buffer entry points (hm_encrypt, hm_decrypt, hm_apply2_host,
  * upload/download): pageable memory works too, but is staged by the driver. NULL on failure. */
 void *hm_host_alloc(size_t bytes);

@@ -230,3 +230,109 @@ def test_mulrem_fresh(oracle, hm, params, n):
     # separate mul then rem agrees with the fused kernel
     two = ctx.poly_rem(ctx.poly_mul(ca, cb))
     np.testing.assert_array_equal(two.to_host(), r.to_host())
+
+
+@pytest.mark.parametrize("dtype,n", [(np.uint64, 3), (np.int32, 17), (np.int8, 40), (np.int64, 2)])
+def test_add_other_widths_and_signed(oracle, hm, dtype, n):
+    """u64 (uint.rs:210-230, ignored there as 'long test') and the signed types: addition of iN is the same circuit
+    on the same bits (int.rs:71-73), so -20 + 22 == 2 (int.rs:187-191)."""
+    rng = np.random.default_rng(77)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 55)
+    info = np.iinfo(dtype)
+    L = np.dtype(dtype).itemsize * 8
+    a = rng.integers(info.min // 2, info.max // 2, size=n, dtype=dtype)
+    b = rng.integers(info.min // 2, info.max // 2, size=n, dtype=dtype)
+    if info.min < 0:
+        a[0], b[0] = 22, -20
+    ma, mb = masks_for(rng, n, L, 128), masks_for(rng, n, L, 128)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    r = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+    u = np.dtype(f"u{np.dtype(dtype).itemsize}")
+    oa, ob = oracle_encrypt(oracle, pk, a.view(u), ma), oracle_encrypt(oracle, pk, b.view(u), mb)
+    want, _ = oracle.apply(oracle.OP_ADD, oa, ob, L, threads=oracle.max_threads())
+    np.testing.assert_array_equal(r.to_host(), expected_padded(want, n, r.slot_words()))
+    dec = ctx.decrypt(r)
+    od, _ = oracle.decrypt(sk, want, L)
+    np.testing.assert_array_equal(dec.view(np.uint8), od)
+    assert dec.dtype == np.dtype(dtype)
+    if info.min < 0:
+        assert int(dec[0]) == 2
+
+
+def test_mul_signed_i8(oracle, hm):
+    """mul_signed_internal (common.rs:115-155; int.rs:248-268 at (512,64,1,64)): 6 * -7 = -42, 0 * 10 = 0.  The two
+    extra XORs with `one` land in the last column and cancel, so the unsigned circuit gives the same polynomials."""
+    rng = np.random.default_rng(5)
+    params = (512, 64, 1, 64)
+    sk, pk, ctx = setup(oracle, hm, params, 66)
+    a = np.array([6, 0, -3, 11], dtype=np.int8)
+    b = np.array([-7, 10, -5, -11], dtype=np.int8)
+    n, L = a.size, 8
+    ma, mb = masks_for(rng, n, L, 64), masks_for(rng, n, L, 64)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    r = ctx.apply2(hm.HomomorphicMultiplication, ca, cb)
+    oa, ob = oracle_encrypt(oracle, pk, a.view(np.uint8), ma), oracle_encrypt(oracle, pk, b.view(np.uint8), mb)
+    want, _ = oracle.apply(oracle.OP_MUL_SIGNED, oa, ob, L, threads=oracle.max_threads())
+    np.testing.assert_array_equal(r.to_host(), expected_padded(want, n, r.slot_words()))
+    dec = ctx.decrypt(r)
+    assert list(dec[:2]) == [-42, 0]
+    np.testing.assert_array_equal(dec, a * b)
+
+
+def test_ragged_and_mismatched_batches(oracle, hm):
+    """Edge cases: operands of different widths (xor of a fresh batch with a product), mismatched n / L rejected."""
+    rng = np.random.default_rng(3)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 4)
+    n, L = 9, 8
+    a = rng.integers(0, 256, size=n, dtype=np.uint8)
+    b = rng.integers(0, 256, size=n, dtype=np.uint8)
+    ma, mb = masks_for(rng, n, L, 128), masks_for(rng, n, L, 128)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
+    prod = ctx.apply2(hm.HomomorphicAndGate, ca, cb)          # 9-word slots
+    mixed = ctx.apply2(hm.HomomorphicXorGate, prod, ca)       # 9-word xor 5-word
+    oprod, _ = oracle.apply(oracle.OP_AND, oa, ob, L)
+    omixed, _ = oracle.apply(oracle.OP_XOR, oprod, oa, L)
+    np.testing.assert_array_equal(mixed.to_host(), expected_padded(omixed, n, mixed.slot_words()))
+    # (a & b) & a : 9-word x 5-word products
+    p3 = ctx.apply2(hm.HomomorphicAndGate, prod, ca)
+    op3, _ = oracle.apply(oracle.OP_AND, oprod, oa, L)
+    np.testing.assert_array_equal(p3.to_host(), expected_padded(op3, n, p3.slot_words()))
+    # add on non-fresh operands takes the generic path and still matches
+    s = ctx.apply2(hm.HomomorphicAddition, prod, cb)
+    os_, _ = oracle.apply(oracle.OP_ADD, oprod, ob, L)
+    np.testing.assert_array_equal(s.to_host(), expected_padded(os_, n, s.slot_words()))
+    other = ctx.encrypt(a[:4], ma[: 4 * L * 16])
+    with pytest.raises(hm.EngineError):
+        ctx.apply2(hm.HomomorphicXorGate, ca, other)
+    wide = ctx.encrypt(a.astype(np.uint16), masks_for(rng, n, 16, 128))
+    with pytest.raises(hm.EngineError):
+        ctx.apply2(hm.HomomorphicXorGate, ca, wide)
+
+
+def test_wire_format_and_canonical_export(oracle, hm):
+    rng = np.random.default_rng(8)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 12)
+    n = 5
+    a = rng.integers(0, 2**16, size=n, dtype=np.uint16)
+    b = rng.integers(0, 2**16, size=n, dtype=np.uint16)
+    ma, mb = masks_for(rng, n, 16, 128), masks_for(rng, n, 16, 128)
+    s = ctx.apply2(hm.HomomorphicAddition, ctx.encrypt(a, ma), ctx.encrypt(b, mb))
+    blob = s.to_bytes()
+    assert blob[:4] == b"HMB1" and len(blob) == 24 + 16 * 8 + n * s.value_words * 8
+    back = hm.Ciphered.from_bytes(ctx, blob)
+    np.testing.assert_array_equal(back.to_host(), s.to_host())
+    np.testing.assert_array_equal(back.slot_degree_bounds(), s.slot_degree_bounds())
+    np.testing.assert_array_equal(ctx.decrypt(back, np.uint16), a + b)
+    other = hm.Context(hm.Parameters(128, 128, 2, 128))
+    with pytest.raises(ValueError):
+        hm.Ciphered.from_bytes(other, blob)
+    with pytest.raises((hm.EngineError, hm.CipherError)):
+        hm.Ciphered.from_bytes(ctx, blob[:-8])
+    # canonical (degree, words) pairs == the oracle's polynomials
+    want, _ = oracle.apply(oracle.OP_ADD, oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb), 16)
+    can = s.canonical()
+    assert len(can) == n * 16
+    for i, (deg, words) in enumerate(can):
+        assert deg == want.degree(i)
+        np.testing.assert_array_equal(words, want.words(i))
