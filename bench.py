@@ -322,6 +322,55 @@ def run_ours(args, rank, local_rank, world):
         extra["encrypt"] = {"value": n / s, "unit": "u32/s", "kernel": "encrypt_tab_kernel<5,4,8>", "ms": s * 1e3,
                             "hbm_GBps": n * 1792 / s / 1e9, "hbm_frac": n * 1792 / s / 1e9 / hbm_peak}
         ce.free()
+        # config 4: u8 homomorphic multiply (column circuit, common.rs:66-105) on 2^14 pairs, then decrypt
+        n8 = 1 << 14
+        g8 = np.random.default_rng(8)
+        a8 = g8.integers(0, 256, size=n8, dtype=np.uint8)
+        b8 = g8.integers(0, 256, size=n8, dtype=np.uint8)
+        c8a = ctx.encrypt(a8, np.frombuffer(g8.bytes(n8 * 8 * 16), dtype=np.uint8))
+        c8b = ctx.encrypt(b8, np.frombuffer(g8.bytes(n8 * 8 * 16), dtype=np.uint8))
+        l0 = ctx.kernel_launches()
+        t0 = time.perf_counter()
+        p8 = ctx.apply2(hm.HomomorphicMultiplication, c8a, c8b)
+        ctx.synchronize()
+        t1 = time.perf_counter()
+        p8b = ctx.apply2(hm.HomomorphicMultiplication, c8a, c8b)
+        ctx.synchronize()
+        t2 = time.perf_counter()
+        d8 = ctx.decrypt(p8b)
+        extra["u8_mul"] = {"value": n8 / (t2 - t1), "unit": "u8 muls/s", "pairs": n8, "ms": (t2 - t1) * 1e3, "first_call_ms": (t1 - t0) * 1e3,
+                           "kernel_launches": int((ctx.kernel_launches() - l0) // 2), "correct_frac": float(np.mean(d8 == a8 * b8)),
+                           "note": "host-planned sequence of generic mul/xor kernels over a per-value arena in HBM; wall clock incl. launches"}
+        for o8 in (p8, p8b, c8a, c8b):
+            o8.free()
+        # config 5 (stress): d=d'=512, tau=256, delta=8 fused mul+rem on 2^20 fresh pairs
+        rb = np.random.default_rng(55)
+        ctxb = hm.Context(hm.Parameters(512, 512, 8, 256), device=local_rank)
+        skb = hm.SecretKey.random(512, rb)
+        ctxb.set_secret_key(skb)
+        ctxb.set_public_key(hm.PublicKey.random(512, 8, 256, skb, rb))
+        nb = 1 << 17  # u8 values -> 2^20 pairs
+        vb1 = rb.integers(0, 256, size=nb, dtype=np.uint8)
+        vb2 = rb.integers(0, 256, size=nb, dtype=np.uint8)
+        cb1 = ctxb.encrypt(vb1, np.frombuffer(rb.bytes(nb * 8 * 32), dtype=np.uint8))
+        cb2 = ctxb.encrypt(vb2, np.frombuffer(rb.bytes(nb * 8 * 32), dtype=np.uint8))
+        mrb = ctxb.poly_mulrem(cb1, cb2)
+        streamb = torch.cuda.ExternalStream(lib.hm_context_stream(ctxb._h), device=torch.device("cuda", local_rank))
+        ctxb.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(streamb)
+        for _ in range(5):
+            assert lib.hm_poly_mulrem_into(ctxb._h, cb1._h, cb2._h, mrb._h) == 0
+        e1.record(streamb)
+        ctxb.synchronize()
+        sb = e0.elapsed_time(e1) * 1e-3 / 5
+        extra["mulrem_config_b"] = {"metric": "GF(2)[X] mul+rem/s (d=d'=512, tau=256, delta=8)", "value": nb * 8 / sb, "unit": "mul+rem/s",
+                                    "kernel": "mulrem_fresh_kernel<32,16>", "pairs_per_launch": nb * 8, "ms": sb * 1e3,
+                                    "Tbitmac_per_s": nb * 8 * (1050625 + 788481) / sb / 1e12,
+                                    "alu_frac": nb * 8 * (1050625 + 788481) / sb / (lane_ops.value * 32.0)}
+        for ob in (cb1, cb2, mrb):
+            ob.free()
+        ctxb.close()
         # PCIe copy rates of this box (the ceiling of every host-buffer call)
         hp = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
         dp_ = torch.empty(1 << 30, dtype=torch.uint8, device=f"cuda:{local_rank}")

@@ -244,26 +244,87 @@ int ensure_ops(hm_context *ctx, size_t n_ops) {
 
 // ---- kernel launch wrappers --------------------------------------------------------------------
 
-int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops, size_t n) {
-    if (ops.empty() || n == 0) return HM_OK;
-    int rc = ensure_ops(ctx, ops.size());
+// Shape class of a product: 0 = general (warp per product); otherwise NX*100+NY (32-bit words) for the
+// thread-per-product Karatsuba kernels, which need "whole blocks + the single top coefficient" operands.
+int mul_shape_class(const MulOp &o) {
+    auto blocks = [](const View &v) -> int { // low words if deg == 64 * (w - 1) and that is 256, 512 or 1024
+        if (v.deg != (uint64_t)64 * (v.w - 1)) return 0;
+        if (v.deg == 256) return 8;
+        if (v.deg == 512) return 16;
+        if (v.deg == 1024) return 32;
+        return 0;
+    };
+    const int nx = blocks(o.a), ny = blocks(o.b);
+    if (!nx || !ny) return 0;
+    if (o.o.w < (uint32_t)((nx + ny) / 2 + 1)) return 0;
+    if ((nx == 8) != (ny == 8)) return 0; // 8-word blocks only pair with 8-word blocks
+    if (nx == 32 && ny == 32) return 0;    // too many live registers for one thread: warp kernel
+    return nx * 100 + ny;
+}
+
+int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, size_t cnt, size_t n, size_t smem_general,
+                     uint32_t per_warp_general) {
+    const dim3 grid_t((unsigned)((n + 127) / 128), (unsigned)cnt);
+    switch (cls) {
+        case 808: hmk::mul_small_kernel<8, 8><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
+        case 1616: hmk::mul_small_kernel<16, 16><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
+        case 1632: hmk::mul_small_kernel<16, 32><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
+        case 3216: hmk::mul_small_kernel<32, 16><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
+        default: {
+            const dim3 grid_w((unsigned)((n + 3) / 4), (unsigned)cnt);
+            static const int old_generic = getenv("HM_MUL_OLD") ? atoi(getenv("HM_MUL_OLD")) : 0;
+            if (old_generic) {
+                CK(cudaFuncSetAttribute(hmk::mul_views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_general));
+                hmk::mul_views_kernel<<<grid_w, hmk::MUL_WARPS * 32, smem_general, ctx->stream>>>(d_ops, n, per_warp_general);
+            } else {
+                CK(cudaFuncSetAttribute(hmk::mul_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_general));
+                hmk::mul_warp_kernel<<<grid_w, 128, smem_general, ctx->stream>>>(d_ops, n, per_warp_general);
+            }
+        }
+    }
+    return post_launch(ctx, "mul kernel");
+}
+
+int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n) {
+    if (ops_in.empty() || n == 0) return HM_OK;
+    // group by shape class (stable), one launch per class
+    std::vector<MulOp> ops(ops_in);
+    static const int no_small = getenv("HM_MUL_NO_SMALL") ? atoi(getenv("HM_MUL_NO_SMALL")) : 0;
+    std::vector<int> cls(ops.size());
+    for (size_t i = 0; i < ops.size(); ++i) cls[i] = no_small ? 0 : mul_shape_class(ops[i]);
+    std::vector<size_t> order(ops.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return cls[x] < cls[y]; });
+    std::vector<MulOp> sorted(ops.size());
+    std::vector<int> scls(ops.size());
+    for (size_t i = 0; i < order.size(); ++i) {
+        sorted[i] = ops[order[i]];
+        scls[i] = cls[order[i]];
+    }
+    int rc = ensure_ops(ctx, sorted.size());
     if (rc != HM_OK) return rc;
-    // stream-ordered: descriptors are copied before the kernel that reads them; the host vector
-    // must stay alive until the copy is done, so synchronise the copy (tiny).
-    CK(cudaMemcpyAsync(ctx->d_ops, ops.data(), ops.size() * sizeof(MulOp), cudaMemcpyHostToDevice, ctx->stream));
+    // stream-ordered: descriptors are copied before the kernels that read them; the host vector must stay alive
+    // until the copy is done, so synchronise the copy (tiny).
+    CK(cudaMemcpyAsync(ctx->d_ops, sorted.data(), sorted.size() * sizeof(MulOp), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    uint32_t per_warp = 0;
-    for (const MulOp &o : ops) per_warp = std::max(per_warp, 2 * (o.a.w + o.b.w));
-    per_warp = (per_warp + 3) & ~3u;
-    const size_t smem = (size_t)per_warp * 4 * hmk::MUL_WARPS;
-    if (smem > ctx->smem_optin) return HM_ERR_UNSUPPORTED;
-    CK(cudaFuncSetAttribute(hmk::mul_views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // gridDim.y is limited to 65535 ops per launch
-    for (size_t first = 0; first < ops.size(); first += 65535) {
-        const size_t cnt = std::min<size_t>(65535, ops.size() - first);
-        dim3 grid((unsigned)((n + hmk::MUL_WARPS - 1) / hmk::MUL_WARPS), (unsigned)cnt);
-        hmk::mul_views_kernel<<<grid, hmk::MUL_WARPS * 32, smem, ctx->stream>>>(ctx->d_ops + first, n, per_warp);
-        LAUNCHED("mul_views_kernel");
+    for (size_t first = 0; first < sorted.size();) {
+        size_t last = first;
+        while (last < sorted.size() && scls[last] == scls[first] && last - first < 65535) ++last;
+        uint32_t per_warp = 0;
+        size_t smem = 0;
+        if (scls[first] == 0) {
+            for (size_t i = first; i < last; ++i) {
+                const uint32_t na = 2 * std::min(sorted[i].a.w, sorted[i].b.w), nc = 2 * std::max(sorted[i].a.w, sorted[i].b.w);
+                const uint32_t nch = (na + hmk::MW_J - 1) / hmk::MW_J;
+                per_warp = std::max(per_warp, std::max(nch * 32 + nch * hmk::MW_J + nc, na + nc));
+            }
+            per_warp = (per_warp + 3) & ~3u;
+            smem = (size_t)per_warp * 4 * 4;
+            if (smem > ctx->smem_optin) return HM_ERR_UNSUPPORTED;
+        }
+        rc = launch_mul_class(ctx, scls[first], ctx->d_ops + first, last - first, n, smem, per_warp);
+        if (rc != HM_OK) return rc;
+        first = last;
     }
     return HM_OK;
 }
@@ -315,6 +376,7 @@ View slot_view(const hm_batch *b, uint32_t k) {
     v.stride = b->value_words;
     v.off = b->off[k];
     v.w = b->w[k];
+    v.deg = b->degb[k];
     return v;
 }
 View null_view() {
@@ -323,6 +385,7 @@ View null_view() {
     v.stride = 0;
     v.off = 0;
     v.w = 0;
+    v.deg = 0;
     return v;
 }
 
@@ -367,6 +430,7 @@ struct PolyRef {
         v.stride = stride;
         v.off = off;
         v.w = zero ? 1u : (uint32_t)std::min<uint64_t>(w_alloc, degb / 64 + 1);
+        v.deg = zero ? 0 : degb;
         return v;
     }
 };
@@ -1083,6 +1147,7 @@ static int add_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
         v.stride = arena_words;
         v.off = i * wmax;
         v.w = (uint32_t)(degb / 64 + 1);
+        v.deg = degb;
         return v;
     };
     int rc = HM_OK;
@@ -1236,6 +1301,7 @@ static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
         v.stride = arena_words;
         v.off = ob.off;
         v.w = (uint32_t)(ob.degb / 64 + 1);
+        v.deg = ob.degb;
         return v;
     };
     auto rview = [&](const Obj &ob) {
@@ -1244,6 +1310,7 @@ static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
         v.stride = o->value_words;
         v.off = ob.off;
         v.w = (uint32_t)std::min<uint64_t>(ob.w_alloc, ob.degb / 64 + 1);
+        v.deg = ob.degb;
         return v;
     };
     int rc = HM_OK;
@@ -1265,6 +1332,7 @@ static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
             r.stride = o->value_words;
             r.off = o->off[st.res_i];
             r.w = o->w[st.res_i];
+            r.deg = o->degb[st.res_i];
             View x = aview(st.x);
             // r ^= x over x's width only (words above are untouched)
             View rr = r;

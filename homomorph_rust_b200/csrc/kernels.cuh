@@ -35,6 +35,7 @@ struct View { // one slot of every value of some buffer
     uint64_t stride; // u64 words between consecutive values
     uint32_t off;    // u64 word offset of the slot inside a value
     uint32_t w;      // slot width in u64 words
+    uint64_t deg;    // degree bound of the polynomials in this slot (host bookkeeping; picks the kernel)
 };
 
 struct MulOp {
@@ -603,6 +604,167 @@ __device__ __forceinline__ void clmul_kara(const uint32_t (&a)[N], const uint32_
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) r[H + i] ^= p1[i] ^ p0[i] ^ p2[i];
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// K4a  small balanced products, one THREAD per product: operands of NX / NY low words plus the single coefficient
+// X^(32 NX) / X^(32 NY) (fresh ciphertexts and their first products: degree bound an exact multiple of 256).
+// Karatsuba on the multiplier in 8- or 16-word blocks.  Used for gate_and / gate_or and for the partial products and
+// early carries of the multiplier circuit.
+// ----------------------------------------------------------------------------------------
+template <int NX, int NY>
+__global__ void __launch_bounds__(128) mul_small_kernel(const MulOp *__restrict__ ops, uint64_t n) {
+    constexpr int K = (NX == 8) ? 8 : 16; // Karatsuba block
+    static_assert(NX % K == 0 && NY % K == 0, "operands are whole blocks");
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const MulOp op = ops[blockIdx.y];
+    const uint64_t *gx = op.a.base + v * op.a.stride + op.a.off;
+    const uint64_t *gy = op.b.base + v * op.b.stride + op.b.off;
+    uint32_t x[NX], y[NY];
+#pragma unroll
+    for (int j = 0; j < NX / 2; ++j) {
+        const uint64_t t = gx[j];
+        x[2 * j] = (uint32_t)t;
+        x[2 * j + 1] = (uint32_t)(t >> 32);
+    }
+#pragma unroll
+    for (int j = 0; j < NY / 2; ++j) {
+        const uint64_t t = gy[j];
+        y[2 * j] = (uint32_t)t;
+        y[2 * j + 1] = (uint32_t)(t >> 32);
+    }
+    const uint32_t xt = (uint32_t)gx[NX / 2] & 1u, yt = (uint32_t)gy[NY / 2] & 1u;
+    uint32_t r[NX + NY + 2];
+#pragma unroll
+    for (int i = 0; i < NX + NY + 2; ++i) r[i] = 0;
+#pragma unroll
+    for (int bx = 0; bx < NX / K; ++bx) {
+#pragma unroll
+        for (int by = 0; by < NY / K; ++by) {
+            uint32_t xa[K], yb[K], t[2 * K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                xa[i] = x[bx * K + i];
+                yb[i] = y[by * K + i];
+            }
+            clmul_kara<K>(xa, yb, t);
+#pragma unroll
+            for (int i = 0; i < 2 * K; ++i) r[(bx + by) * K + i] ^= t[i];
+        }
+    }
+    const uint32_t mx = 0u - xt, my = 0u - yt;
+#pragma unroll
+    for (int j = 0; j < NY; ++j) r[NX + j] ^= y[j] & mx;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) r[NY + j] ^= x[j] & my;
+    r[NX + NY] ^= xt & yt;
+    uint64_t *go = op.o.base + v * op.o.stride + op.o.off;
+#pragma unroll
+    for (int j = 0; j < (NX + NY) / 2 + 1; ++j)
+        if ((uint32_t)j < op.o.w) go[j] = (uint64_t)r[2 * j] | ((uint64_t)r[2 * j + 1] << 32);
+    for (uint32_t j = (NX + NY) / 2 + 1; j < op.o.w; ++j) go[j] = 0;
+}
+
+// ----------------------------------------------------------------------------------------
+// K4b  general products, one WARP per product (the carry-chain machinery of the fused adder, for any two widths).
+// The shorter operand a is the multiplier: it is cut into chunks of 24 words whose bits are transposed once
+// (Bt[chunk][s] = which words of the chunk have bit s set) so that every lane sees them as warp-uniform masks; the
+// longer operand c sits in shared memory; each lane owns TQ output words per pass and, per chunk, runs the Horner
+// recurrence over s with one halo word (see adder_step_pass), skipping the zero bits of a.
+// ----------------------------------------------------------------------------------------
+constexpr int MW_J = 24;
+
+template <int TQ>
+__device__ __forceinline__ void mul_warp_pass(const uint32_t *__restrict__ sc, int nc, const uint32_t *__restrict__ sBt,
+                                              int nchunks, int w0, int no, uint32_t *__restrict__ gout, int lane) {
+    uint32_t tot[TQ];
+#pragma unroll
+    for (int i = 0; i < TQ; ++i) tot[i] = 0;
+    const int t0 = w0 + lane * TQ;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int j0 = ch * MW_J;
+        // warp-uniform skip: the union of this pass's windows is [w0 - j0 - J, w0 + 32 TQ - j0)
+        if (w0 + 32 * TQ - j0 <= 0 || w0 - j0 - MW_J >= nc) continue;
+        const uint32_t Bmine = sBt[ch * 32 + lane];
+        if (__ballot_sync(FULL, Bmine != 0u) == 0u) continue;
+        uint32_t win[MW_J + TQ], acc[TQ + 1];
+        const int base = t0 - j0 - MW_J;
+#pragma unroll
+        for (int y = 0; y < MW_J + TQ; ++y) {
+            const int idx = base + y;
+            win[y] = (idx >= 0 && idx < nc) ? sc[idx] : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i <= TQ; ++i) acc[i] = 0;
+#pragma unroll 1
+        for (int s = 31; s >= 0; --s) {
+            const uint32_t Bs = __shfl_sync(FULL, Bmine, s);
+#pragma unroll
+            for (int i = TQ; i > 0; --i) acc[i] = __funnelshift_l(acc[i - 1], acc[i], 1);
+            acc[0] <<= 1;
+#pragma unroll
+            for (int j = 0; j < MW_J; ++j) {
+                if ((Bs >> j) & 1u) {
+#pragma unroll
+                    for (int i = 0; i <= TQ; ++i) acc[i] ^= win[i + MW_J - 1 - j];
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) tot[i] ^= acc[i + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < TQ; ++i)
+        if (t0 + i < no) gout[t0 + i] = tot[i];
+}
+
+static __global__ void __launch_bounds__(128, 4) mul_warp_kernel(const MulOp *__restrict__ ops, uint64_t n, uint32_t smem_words_per_warp) {
+    extern __shared__ __align__(16) uint32_t smem32[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t v = (uint64_t)blockIdx.x * 4 + warp;
+    if (v >= n) return;
+    const MulOp op = ops[blockIdx.y];
+    const uint32_t *ga = reinterpret_cast<const uint32_t *>(op.a.base + v * op.a.stride + op.a.off);
+    const uint32_t *gc = reinterpret_cast<const uint32_t *>(op.b.base + v * op.b.stride + op.b.off);
+    int na = 2 * (int)op.a.w, nc = 2 * (int)op.b.w;
+    if (na > nc) { // the shorter operand is the multiplier
+        const uint32_t *tp = ga; ga = gc; gc = tp;
+        const int tn = na; na = nc; nc = tn;
+    }
+    const int nchunks = (na + MW_J - 1) / MW_J;
+    uint32_t *sBt = smem32 + (size_t)warp * smem_words_per_warp; // nchunks x 32
+    uint32_t *sa = sBt + nchunks * 32;                           // nchunks x MW_J (zero padded)
+    uint32_t *sc = sa + nchunks * MW_J;                          // nc
+    for (int i = lane; i < nchunks * MW_J; i += 32) sa[i] = (i < na) ? ga[i] : 0u;
+    for (int i = lane; i < nc; i += 32) sc[i] = gc[i];
+    __syncwarp();
+    for (int ch = 0; ch < nchunks; ++ch) { // transpose: lane s collects bit s of the chunk's words
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < MW_J; ++j) m |= ((sa[ch * MW_J + j] >> lane) & 1u) << j;
+        sBt[ch * 32 + lane] = m;
+    }
+    __syncwarp();
+    uint32_t *gout = reinterpret_cast<uint32_t *>(op.o.base + v * op.o.stride + op.o.off);
+    const int no = 2 * (int)op.o.w;
+    int w0 = 0;
+    while (w0 < no) {
+        const int left = no - w0;
+        if (left > 32 * 16) {
+            mul_warp_pass<24>(sc, nc, sBt, nchunks, w0, no, gout, lane);
+            w0 += 32 * 24;
+        } else if (left > 32 * 8) {
+            mul_warp_pass<16>(sc, nc, sBt, nchunks, w0, no, gout, lane);
+            w0 += 32 * 16;
+        } else if (left > 32 * 2) {
+            mul_warp_pass<8>(sc, nc, sBt, nchunks, w0, no, gout, lane);
+            w0 += 32 * 8;
+        } else {
+            mul_warp_pass<2>(sc, nc, sBt, nchunks, w0, no, gout, lane);
+            w0 += 32 * 2;
+        }
     }
 }
 
