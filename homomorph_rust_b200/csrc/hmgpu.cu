@@ -72,6 +72,7 @@ struct hm_context {
     uint32_t enc_wb = 0, enc_groups = 0, enc_table_words = 0;
     bool enc_table_in_smem = false;
     uint64_t *d_enc_table = nullptr;
+    uint64_t *d_enc_table6 = nullptr; // bank-partitioned copy for encrypt_tab6_kernel (config A shape only)
 
     // scratch for op descriptors
     MulOp *d_ops = nullptr;
@@ -227,7 +228,9 @@ void clear_secret(hm_context *ctx) {
 
 void clear_public(hm_context *ctx) {
     if (ctx->d_enc_table) cudaFree(ctx->d_enc_table);
+    if (ctx->d_enc_table6) cudaFree(ctx->d_enc_table6);
     ctx->d_enc_table = nullptr;
+    ctx->d_enc_table6 = nullptr;
     ctx->has_pk = false;
     ctx->enc_table_words = 0;
 }
@@ -620,6 +623,17 @@ int hm_set_public_key(hm_context *ctx, const uint8_t *const *polys, const size_t
     CK(cudaMalloc(&ctx->d_enc_table, tab.size() * 8));
     CK(cudaMemcpyAsync(ctx->d_enc_table, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (in_smem && wb == 8 && wf == 5 && tau == 128 && (size_t)hmk::ENC6_SLOTS * 256 * 128 + 1024 <= ctx->smem_optin) {
+        // line(t, e): rows of groups 3t, 3t+1, 3t+2 at 64-bit word offsets 0, 5, 10 of a 16-word line
+        std::vector<uint64_t> t6((size_t)hmk::ENC6_SLOTS * 256 * 16, 0);
+        for (uint32_t g = 0; g < groups; ++g)
+            for (uint32_t e = 0; e < 256; ++e)
+                for (uint32_t j = 0; j < 5; ++j)
+                    t6[((size_t)(g / 3) * 256 + e) * 16 + 5 * (g % 3) + j] = tab[((size_t)(g << 8) + e) * 5 + j];
+        CK(cudaMalloc(&ctx->d_enc_table6, t6.size() * 8));
+        CK(cudaMemcpyAsync(ctx->d_enc_table6, t6.data(), t6.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->enc_wb = wb;
     ctx->enc_groups = groups;
     ctx->enc_table_words = (uint32_t)tab.size();
@@ -899,7 +913,14 @@ static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint
     if (ctx->enc_table_in_smem && masks_aligned && p.wf == 17 && ctx->tau == 256 && p.wb == 4 &&
         table_bytes + 2 * (size_t)hmk::ENC_THREADS * 17 * 8 <= ctx->smem_optin)
         path = 2;
-    if (path == 1) {
+    static const int enc_mode = getenv("HM_ENC_MODE") ? atoi(getenv("HM_ENC_MODE")) : 1;
+    if (path == 1 && enc_mode == 1 && ctx->d_enc_table6) {
+        const size_t smem = (size_t)hmk::ENC6_SLOTS * 256 * 128;
+        CK(cudaFuncSetAttribute(hmk::encrypt_tab6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = grid_for(ctx, (p.units + 5) / 6 * 32, hmk::ENC6_THREADS, 1);
+        hmk::encrypt_tab6_kernel<<<grid, hmk::ENC6_THREADS, smem, ctx->stream>>>(p, ctx->d_enc_table6);
+        LAUNCHED("encrypt_tab6_kernel");
+    } else if (path == 1) {
         const size_t smem = table_bytes + 2 * (size_t)hmk::ENC_THREADS * 5 * 8;
         auto kern = hmk::encrypt_tab_kernel<5, 4, 8>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

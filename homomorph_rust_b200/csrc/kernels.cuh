@@ -190,6 +190,73 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encrypt_tab_kernel(EncParams p
     if (tid == 0) tma_store_wait_all();
 }
 
+// Config-A fast path (tau = 128, 8-bit windows, 40-byte rows): 5 lanes per bit-ciphertext (one 64-bit word of the
+// row each), 6 bit-ciphertexts per warp iteration, and a BANK-PARTITIONED table: window groups are split in three
+// classes (g mod 3); the rows of class r live at byte offset 40 r of a 128-byte line, i.e. in shared-memory banks
+// [10 r, 10 r + 10).  The three ciphertexts that share a half-warp always read three different classes (rotation
+// by their position), so a warp-wide LDS.64 is conflict-free whatever the (random) row indices are.
+//   line(t, e) = 128 bytes: [ row(group 3t, e) | row(group 3t+1, e) | row(group 3t+2, e) | 8 B pad ],  t = 0..5
+// (groups 16, 17 do not exist: zero rows).  192 KB of shared memory, one persistent 1024-thread CTA per SM.
+constexpr int ENC6_THREADS = 1024;
+constexpr int ENC6_SLOTS = 6;
+static __global__ void __launch_bounds__(ENC6_THREADS, 1) encrypt_tab6_kernel(EncParams p, const uint64_t *__restrict__ table6) {
+    extern __shared__ __align__(16) uint64_t smem64[];
+    uint64_t *tab = smem64; // ENC6_SLOTS * 256 * 16 words
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(table6);
+        uint4 *dst = reinterpret_cast<uint4 *>(tab);
+        for (uint32_t i = tid; i < ENC6_SLOTS * 256 * 8; i += ENC6_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    // lanes 0-14: ciphertexts 0,1,2 of the group; lanes 16-30: ciphertexts 3,4,5; lanes 15 and 31 idle
+    const uint32_t hl = lane & 15, r = hl / 5, j = hl - r * 5, c = r + 3 * (lane >> 4);
+    const bool active = hl < 15;
+    // 64-bit word offset inside a line for rotation step k: class (r + k) % 3 at words 5*class, plus my word j
+    const uint32_t o0 = 5 * ((r + 0) % 3) + j, o1 = 5 * ((r + 1) % 3) + j, o2 = 5 * ((r + 2) % 3) + j;
+    const uint32_t rot = 8 * r;
+    const uint64_t ngroups = (p.units + 5) / 6;
+    const uint64_t wstride = (uint64_t)gridDim.x * (ENC6_THREADS / 32);
+    uint64_t g6 = (uint64_t)blockIdx.x * (ENC6_THREADS / 32) + warp;
+    uint4 m_nxt = make_uint4(0, 0, 0, 0);
+    uint32_t b_nxt = 0;
+    if (g6 < ngroups) {
+        const uint64_t u = g6 * 6 + c;
+        if (active && u < p.units) {
+            m_nxt = __ldg(reinterpret_cast<const uint4 *>(p.masks) + u);
+            b_nxt = __ldg(p.values + (u >> 3));
+        }
+    }
+    for (; g6 < ngroups; g6 += wstride) {
+        const uint64_t u = g6 * 6 + c;
+        const uint4 m4 = m_nxt;
+        const uint32_t pb = b_nxt;
+        {
+            const uint64_t un = (g6 + wstride) * 6 + c;
+            if (g6 + wstride < ngroups && active && un < p.units) {
+                m_nxt = __ldg(reinterpret_cast<const uint4 *>(p.masks) + un);
+                b_nxt = __ldg(p.values + (un >> 3));
+            }
+        }
+        if (!active || u >= p.units) continue;
+        const uint32_t mk[5] = {m4.x, m4.y, m4.z, m4.w, 0u};
+        uint64_t acc = 0;
+#pragma unroll
+        for (int t = 0; t < ENC6_SLOTS; ++t) {
+            // F = mask bytes 3t, 3t+1, 3t+2 (24 bits), rotated left by my position so that byte k is group 3t + (r+k)%3
+            const int bit = 24 * t, w = bit >> 5, sh = bit & 31;
+            uint32_t F = __funnelshift_r(mk[w], mk[w + 1 > 4 ? 4 : w + 1], sh) & 0xffffffu;
+            F = ((F >> rot) | (F << (24 - rot))) & 0xffffffu; // rotate right by 8r: byte k <- byte (k + r) % 3
+            const uint64_t *line = tab + (size_t)t * 256 * 16;
+            acc ^= line[(F & 255u) * 16 + o0];
+            acc ^= line[((F >> 8) & 255u) * 16 + o1];
+            acc ^= line[(F >> 16) * 16 + o2];
+        }
+        if (j == 0) acc ^= (uint64_t)((pb >> (u & 7)) & 1u);
+        p.out[u * 5 + j] = acc;
+    }
+}
+
 // Generic path: any tau / D / window, table read from shared memory if it fits, else from L2.
 static __global__ void __launch_bounds__(256) encrypt_generic_kernel(EncParams p) {
     extern __shared__ __align__(16) uint64_t smem64[];
