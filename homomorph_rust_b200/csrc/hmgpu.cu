@@ -1406,7 +1406,10 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                 if (warps < 1) warps = 1;
                 const size_t smem = per_warp * warps;
                 static const int mode = getenv("HM_ADDER_MODE") ? atoi(getenv("HM_ADDER_MODE")) : 1;
-                auto kern = mode == 2 ? hmk::adder_fused_kernel<8, 2> : (mode == 1 ? hmk::adder_fused_kernel<8, 1> : hmk::adder_fused_kernel<8, 0>);
+                static const int ts = getenv("HM_ADDER_TS") ? atoi(getenv("HM_ADDER_TS")) : 0;
+                auto kern = mode == 0 ? hmk::adder_fused_kernel<8, 0, 0>
+                                      : (ts == 1 ? hmk::adder_fused_kernel<8, 1, 1>
+                                                 : (ts == 2 ? hmk::adder_fused_kernel<8, 1, 2> : hmk::adder_fused_kernel<8, 1, 0>));
                 CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 const unsigned grid = (unsigned)((n + warps - 1) / warps);
                 kern<<<grid, warps * 32, smem, ctx->stream>>>(a->d, b->d, o->d, n, a->L, make_layout(o));

@@ -816,21 +816,59 @@ static __global__ void __launch_bounds__(128, 4) mul_warp_kernel(const MulOp *__
     __syncwarp();
     uint32_t *gout = reinterpret_cast<uint32_t *>(op.o.base + v * op.o.stride + op.o.off);
     const int no = 2 * (int)op.o.w;
+    // Passes of 32 lanes x TQ words.  All warps of a launch run the same shape, so many tile widths cost no
+    // instruction-cache pressure here (unlike the fused adder); up to MW_TAIL trailing words (typically the word that
+    // only holds the leading coefficient) are left to the scalar tail below instead of forcing a wider tile.
+    constexpr int MW_TAIL = 3;
     int w0 = 0;
-    while (w0 < no) {
-        const int left = no - w0;
-        if (left > 32 * 16) {
+    while (no - w0 > MW_TAIL) {
+        const int left = no - w0 - MW_TAIL;
+        if (left > 32 * 20) {
             mul_warp_pass<24>(sc, nc, sBt, nchunks, w0, no, gout, lane);
             w0 += 32 * 24;
-        } else if (left > 32 * 8) {
+        } else if (left > 32 * 16) {
+            mul_warp_pass<20>(sc, nc, sBt, nchunks, w0, no, gout, lane);
+            w0 += 32 * 20;
+        } else if (left > 32 * 12) {
             mul_warp_pass<16>(sc, nc, sBt, nchunks, w0, no, gout, lane);
             w0 += 32 * 16;
-        } else if (left > 32 * 2) {
+        } else if (left > 32 * 8) {
+            mul_warp_pass<12>(sc, nc, sBt, nchunks, w0, no, gout, lane);
+            w0 += 32 * 12;
+        } else if (left > 32 * 6) {
             mul_warp_pass<8>(sc, nc, sBt, nchunks, w0, no, gout, lane);
             w0 += 32 * 8;
+        } else if (left > 32 * 4) {
+            mul_warp_pass<6>(sc, nc, sBt, nchunks, w0, no, gout, lane);
+            w0 += 32 * 6;
+        } else if (left > 32 * 2) {
+            mul_warp_pass<4>(sc, nc, sBt, nchunks, w0, no, gout, lane);
+            w0 += 32 * 4;
         } else {
             mul_warp_pass<2>(sc, nc, sBt, nchunks, w0, no, gout, lane);
             w0 += 32 * 2;
+        }
+    }
+    // scalar tail: output word r = sum_j a[j] * c[r-j] (low half) + a[j] * c[r-j-1] (high half); for the top words
+    // only the top few words of a contribute, so the j range is tiny
+    if (w0 < no) {
+        const int r = w0 + lane;
+        if (r < no) {
+            uint32_t acc = 0;
+            int jlo = r - nc;
+            if (jlo < 0) jlo = 0;
+            for (int j = jlo; j < na && j <= r; ++j) {
+                uint32_t aw = sa[j];
+                const int bi = r - j;
+                const uint32_t hi = (bi < nc) ? sc[bi] : 0u;
+                const uint32_t lo = (bi >= 1 && bi - 1 < nc) ? sc[bi - 1] : 0u;
+                while (aw) {
+                    const int sft = __ffs(aw) - 1;
+                    aw &= aw - 1;
+                    acc ^= __funnelshift_l(lo, hi, sft);
+                }
+            }
+            gout[r] = acc;
         }
     }
 }
@@ -1128,7 +1166,7 @@ __device__ __forceinline__ void adder_step_pass(uint32_t *cbuf, const uint32_t *
     }
 }
 
-template <int WD, int MODE>
+template <int WD, int MODE, int TS>
 __global__ void __launch_bounds__(128, 5) adder_fused_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
                                                              uint64_t *__restrict__ O, uint64_t n, uint32_t L, Layout lo) {
     using C = AdderCfg<WD>;
@@ -1236,10 +1274,21 @@ __global__ void __launch_bounds__(128, 5) adder_fused_kernel(const uint64_t *__r
         constexpr uint32_t FULLW = 32 * 24;
         const uint32_t nfull = (len_next - 1) / FULLW;
         {
+            // tile widths per pass: {8,16,24} (TS=0), {12,24} (TS=1) or {8,24} (TS=2).  Finer sets do less work per step
+            // (work ~ TQ+1) but every extra instantiation is ~8 KB of hot code and the loop is instruction-fetch
+            // sensitive (profiles/README.md): {4,...,24 step 4} measured 18 % SLOWER than {8,16,24}.
             const uint32_t w0 = nfull * FULLW, left = len_next - w0;
-            if (left > 32 * 16) adder_step_pass<WD, 24, MODE>(cb, gk, Bmine, w0, len_next, lane);
-            else if (left > 32 * 8) adder_step_pass<WD, 16, MODE>(cb, gk, Bmine, w0, len_next, lane);
-            else adder_step_pass<WD, 8, MODE>(cb, gk, Bmine, w0, len_next, lane);
+            if constexpr (TS == 0) {
+                if (left > 32 * 16) adder_step_pass<WD, 24, MODE>(cb, gk, Bmine, w0, len_next, lane);
+                else if (left > 32 * 8) adder_step_pass<WD, 16, MODE>(cb, gk, Bmine, w0, len_next, lane);
+                else adder_step_pass<WD, 8, MODE>(cb, gk, Bmine, w0, len_next, lane);
+            } else if constexpr (TS == 1) {
+                if (left > 32 * 12) adder_step_pass<WD, 24, MODE>(cb, gk, Bmine, w0, len_next, lane);
+                else adder_step_pass<WD, 12, MODE>(cb, gk, Bmine, w0, len_next, lane);
+            } else {
+                if (left > 32 * 8) adder_step_pass<WD, 24, MODE>(cb, gk, Bmine, w0, len_next, lane);
+                else adder_step_pass<WD, 8, MODE>(cb, gk, Bmine, w0, len_next, lane);
+            }
         }
         for (uint32_t f = nfull; f-- > 0;) {
             __syncwarp();
