@@ -42,6 +42,9 @@ BITMACS_PER_ADD = 2.751e8        # schoolbook AND-XOR pairs over the 93 referenc
 BYTES_PER_ADD = 2560 + 46912     # 2 x 32 x 5 words in, 5 864 words out
 BITMACS_PER_MULREM = 66049 + 49665
 BYTES_PER_MULREM = 96
+# dram__bytes_read.sum + dram__bytes_write.sum of adder_fused_kernel from the ncu --set full capture in profiles/
+# (r01_adder_ncu_details.txt: 42.3 MB + 711.4 MB for 16 384 adds), per add
+NCU_DRAM_BYTES_PER_ADD = (42.303744e6 + 711.399424e6) / 16384
 
 
 def measured_peaks():
@@ -322,6 +325,18 @@ def run_ours(args, rank, local_rank, world):
         extra["encrypt"] = {"value": n / s, "unit": "u32/s", "kernel": "encrypt_tab6_kernel", "ms": s * 1e3,
                             "hbm_GBps": n * 1792 / s / 1e9, "hbm_frac": n * 1792 / s / 1e9 / hbm_peak}
         ce.free()
+        # gates on fresh u32 batches (gate_xor / gate_and, common.rs:5-27): n*32 bit-ciphertext pairs per launch
+        xo = ctx.apply2(hm.HomomorphicXorGate, ca, cb)
+        s = timed(lambda: lib.hm_apply2_into(ctx._h, N.HM_OP_XOR, ca._h, cb._h, xo._h), reps=20)
+        extra["xor_gate"] = {"value": n * L / s, "unit": "bit-ciphertext xors/s", "kernel": "xor_flat_kernel", "ms": s * 1e3,
+                             "hbm_GBps": n * L * 120 / s / 1e9, "hbm_frac": n * L * 120 / s / 1e9 / hbm_peak}
+        xo.free()
+        ao = ctx.apply2(hm.HomomorphicAndGate, ca, cb)
+        s = timed(lambda: lib.hm_apply2_into(ctx._h, N.HM_OP_AND, ca._h, cb._h, ao._h), reps=5)
+        extra["and_gate"] = {"value": n * L / s, "unit": "bit-ciphertext ands/s", "kernel": "mul_small_kernel<8,8>", "ms": s * 1e3,
+                             "hbm_GBps": n * L * 152 / s / 1e9, "Tbitmac_per_s": n * L * 66049 / s / 1e12,
+                             "alu_frac": n * L * 66049 / s / (lane_ops.value * 32.0)}
+        ao.free()
         # config 4: u8 homomorphic multiply (column circuit, common.rs:66-105) on 2^14 pairs, then decrypt
         n8 = 1 << 14
         g8 = np.random.default_rng(8)
@@ -394,13 +409,17 @@ def run_ours(args, rank, local_rank, world):
         ach = n * BITMACS_PER_ADD / launch_s
         roofline = {"kernel": "adder_fused_kernel<8>", "bound": "alu", "achieved": ach / 1e12, "peak": peak_bitmac / 1e12,
                     "unit": "Tbit-MAC/s", "frac": ach / peak_bitmac, "traffic": None,
+                    "alu_pipe_busy_ncu": 0.918,
                     "peak_source": f"measured in this run: LOP3 issue-rate probe, {lane_ops.value / 1e12:.2f} T lane-ops/s at ~{mhz.value:.0f} MHz (x32 bits)",
                     "note": "achieved counts the reference's schoolbook AND-XOR pairs (SURVEY.md A.2); the kernel skips the zero bits "
                             "of the warp-uniform multiplier and pairs XORs in 3-input LOP3s, so frac can exceed 1"}
         hbm_peak, src = measured_peaks()
         gbs = n * BYTES_PER_ADD / launch_s / 1e9
         roofline_hbm = {"kernel": "adder_fused_kernel<8>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": gbs / hbm_peak, "traffic": None, "peak_source": src}
+                        "frac": gbs / hbm_peak, "traffic": n * NCU_DRAM_BYTES_PER_ADD,
+                        "traffic_source": "ncu --set full capture at 16 384 adds (profiles/r01_adder_ncu_details.txt), scaled per add; "
+                                          "algorithmic bytes per launch = %d" % (n * BYTES_PER_ADD),
+                        "peak_source": src}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the box's host cores ------------------
     cpu = None
@@ -423,7 +442,12 @@ def run_ours(args, rank, local_rank, world):
         _, sec = orc.apply(orc.OP_ADD, oa, ob, L, threads=threads)
         _, sec1 = orc.apply(orc.OP_ADD, orc.PolyVec.from_words([oa.words(i) for i in range(4 * L)]),
                             orc.PolyVec.from_words([ob.words(i) for i in range(4 * L)]), L, threads=1)
-        cpu = {"value": cnt / sec, "unit": UNIT, "cores": threads, "kind": "port",
+        # the second metric of BASELINE.json beside it: mul + rem on fresh pairs (bit-serial mul, long-division rem)
+        mcnt = 65536 * threads // L * L
+        ma_, mb_ = oenc(mcnt // L), oenc(mcnt // L)
+        _, msec = orc.poly_mulrem(ma_, mb_, osk, threads=threads)
+        cpu_mulrem = {"value": mcnt / msec, "unit": "mul+rem/s", "cores": threads, "kind": "port", "sample": f"{mcnt} pairs, {msec:.2f} s"}
+        cpu = {"value": cnt / sec, "unit": UNIT, "cores": threads, "kind": "port", "mulrem": cpu_mulrem,
                "sample": f"{cnt} pairs, {threads} threads over independent values, {sec:.1f} s",
                "single_thread_value": 4 / sec1,
                "published_reference": "README.md:75: 950 us per add = 1053 adds/s, 1 thread of a Ryzen 7 7800X3D"}

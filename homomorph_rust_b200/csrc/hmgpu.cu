@@ -74,9 +74,11 @@ struct hm_context {
     uint64_t *d_enc_table = nullptr;
     uint64_t *d_enc_table6 = nullptr; // bank-partitioned copy for encrypt_tab6_kernel (config A shape only)
 
-    // scratch for op descriptors
+    // ring of op descriptors: pinned host staging + device copy, so that launches need no host synchronisation
     MulOp *d_ops = nullptr;
+    MulOp *h_ops = nullptr;
     size_t d_ops_cap = 0;
+    size_t ops_cursor = 0;
 };
 
 namespace {
@@ -235,13 +237,28 @@ void clear_public(hm_context *ctx) {
     ctx->enc_table_words = 0;
 }
 
-int ensure_ops(hm_context *ctx, size_t n_ops) {
-    if (ctx->d_ops_cap >= n_ops) return HM_OK;
-    if (ctx->d_ops) cudaFree(ctx->d_ops);
-    ctx->d_ops = nullptr;
-    size_t cap = std::max<size_t>(n_ops, 256);
-    CK(cudaMalloc(&ctx->d_ops, cap * sizeof(MulOp)));
-    ctx->d_ops_cap = cap;
+// Reserves n_ops consecutive slots of the descriptor ring and returns the first slot.  Slots are reused only after a
+// wrap-around, which synchronises the stream (every earlier kernel has then consumed its descriptors).
+int ensure_ops(hm_context *ctx, size_t n_ops, size_t *first_slot) {
+    constexpr size_t RING = 16384;
+    if (!ctx->d_ops || ctx->d_ops_cap < n_ops) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_ops) cudaFree(ctx->d_ops);
+        if (ctx->h_ops) cudaFreeHost(ctx->h_ops);
+        ctx->d_ops = nullptr;
+        ctx->h_ops = nullptr;
+        const size_t cap = std::max<size_t>(n_ops, RING);
+        CK(cudaMalloc(&ctx->d_ops, cap * sizeof(MulOp)));
+        CK(cudaHostAlloc(&ctx->h_ops, cap * sizeof(MulOp), cudaHostAllocDefault));
+        ctx->d_ops_cap = cap;
+        ctx->ops_cursor = 0;
+    }
+    if (ctx->ops_cursor + n_ops > ctx->d_ops_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->ops_cursor = 0;
+    }
+    *first_slot = ctx->ops_cursor;
+    ctx->ops_cursor += n_ops;
     return HM_OK;
 }
 
@@ -304,12 +321,13 @@ int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n) 
         sorted[i] = ops[order[i]];
         scls[i] = cls[order[i]];
     }
-    int rc = ensure_ops(ctx, sorted.size());
+    size_t slot = 0;
+    int rc = ensure_ops(ctx, sorted.size(), &slot);
     if (rc != HM_OK) return rc;
-    // stream-ordered: descriptors are copied before the kernels that read them; the host vector must stay alive
-    // until the copy is done, so synchronise the copy (tiny).
-    CK(cudaMemcpyAsync(ctx->d_ops, sorted.data(), sorted.size() * sizeof(MulOp), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // stream-ordered and asynchronous: descriptors go through a pinned ring, so neither the copy nor the kernels
+    // that read them need the host to wait
+    memcpy(ctx->h_ops + slot, sorted.data(), sorted.size() * sizeof(MulOp));
+    CK(cudaMemcpyAsync(ctx->d_ops + slot, ctx->h_ops + slot, sorted.size() * sizeof(MulOp), cudaMemcpyHostToDevice, ctx->stream));
     for (size_t first = 0; first < sorted.size();) {
         size_t last = first;
         while (last < sorted.size() && scls[last] == scls[first] && last - first < 65535) ++last;
@@ -325,7 +343,7 @@ int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n) 
             smem = (size_t)per_warp * 4 * 4;
             if (smem > ctx->smem_optin) return HM_ERR_UNSUPPORTED;
         }
-        rc = launch_mul_class(ctx, scls[first], ctx->d_ops + first, last - first, n, smem, per_warp);
+        rc = launch_mul_class(ctx, scls[first], ctx->d_ops + slot + first, last - first, n, smem, per_warp);
         if (rc != HM_OK) return rc;
         first = last;
     }
@@ -504,6 +522,7 @@ void hm_context_destroy(hm_context *ctx) {
     clear_secret(ctx);
     clear_public(ctx);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
+    if (ctx->h_ops) cudaFreeHost(ctx->h_ops);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1388,6 +1407,24 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
         case HM_OP_AND:
         case HM_OP_OR: {
             std::vector<MulOp> ops;
+            bool flat = same_layout(a, b);
+            for (uint32_t k = 0; k < a->L && flat; ++k)
+                flat = a->w[k] == a->w[0] && a->degb[k] == a->degb[0] && b->degb[k] == b->degb[0] && o->w[k] == o->w[0];
+            if (flat && (uint64_t)n * a->L < ((uint64_t)1 << 40)) {
+                // every slot has the same shape: one product per (value, slot) over the flattened batch, so that
+                // neighbouring threads touch neighbouring memory
+                View va = slot_view(a, 0), vb = slot_view(b, 0), vo = slot_view(o, 0);
+                va.stride = va.w;
+                vb.stride = vb.w;
+                vo.stride = vo.w;
+                ops.push_back(MulOp{va, vb, vo});
+                rc = launch_mul_ops(ctx, ops, n * a->L);
+                if (rc == HM_OK && op == HM_OP_OR) {
+                    rc = launch_xor_views(ctx, vo, vo, va, n * a->L);
+                    if (rc == HM_OK) rc = launch_xor_views(ctx, vo, vo, vb, n * a->L);
+                }
+                break;
+            }
             for (uint32_t k = 0; k < a->L; ++k) ops.push_back(MulOp{slot_view(a, k), slot_view(b, k), slot_view(o, k)});
             rc = launch_mul_ops(ctx, ops, n);
             if (rc == HM_OK && op == HM_OP_OR) { // a + b + a*b, cipher.rs:76-83
@@ -1519,7 +1556,7 @@ int hm_apply2_host(hm_context *ctx, int op, size_t n, uint32_t L, const uint32_t
     // chunked pipeline on three streams: upload of chunk c+1 and download of chunk c-1 overlap the
     // kernels of chunk c.  Two stages of device buffers are allocated once and reused.
     const size_t per_value_bytes = (vwa + vwb + vwo) * 8;
-    size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)384 << 20) / std::max<size_t>(per_value_bytes, 1)));
+    size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)96 << 20) / std::max<size_t>(per_value_bytes, 1)));
     if (chunk > 1024) chunk &= ~(size_t)1023;
     cudaStream_t user = ctx->stream;
     cudaStream_t s_up = nullptr, s_down = nullptr;

@@ -336,3 +336,48 @@ def test_wire_format_and_canonical_export(oracle, hm):
     for i, (deg, words) in enumerate(can):
         assert deg == want.degree(i)
         np.testing.assert_array_equal(words, want.words(i))
+
+
+def test_apply2_host_pipeline(oracle, hm):
+    """hm_apply2_host: host ciphertexts in, host result out, chunked over three streams — equals the device-resident
+    path and the oracle (several chunks: 18 000 u32 adds = 0.9 GB of result)."""
+    import ctypes as C
+
+    from homomorph_rust_b200 import _native as N
+
+    rng = np.random.default_rng(21)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 31)
+    lib = hm.lib()
+    n, L = 18000, 32
+    a = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    b = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    ma = np.frombuffer(rng.bytes(n * L * 16), dtype=np.uint8)
+    mb = np.frombuffer(rng.bytes(n * L * 16), dtype=np.uint8)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    ha, hb = ca.to_host(), cb.to_host()
+    dev = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+    wo = dev.slot_words().astype(np.uint32)
+    wa = np.full(L, 5, dtype=np.uint32)
+    u32p = C.POINTER(C.c_uint32)
+    out = np.zeros((n, int(wo.sum())), dtype=np.uint64)
+    rc = lib.hm_apply2_host(ctx._h, N.HM_OP_ADD, n, L, wa.ctypes.data_as(u32p), ha.ctypes.data, wa.ctypes.data_as(u32p), hb.ctypes.data, out.ctypes.data)
+    assert rc == 0
+    check = np.concatenate([np.arange(0, 64), np.arange(n - 64, n), rng.integers(0, n, 256)])
+    dh = dev.to_host()
+    np.testing.assert_array_equal(out[check], dh[check])
+    assert np.array_equal(out, dh)
+    k = 8
+    want, _ = oracle.apply(oracle.OP_ADD, oracle_encrypt(oracle, pk, a[:k], ma[: k * L * 16]), oracle_encrypt(oracle, pk, b[:k], mb[: k * L * 16]), L,
+                           threads=oracle.max_threads())
+    np.testing.assert_array_equal(out[:k], expected_padded(want, k, wo))
+    # expected result widths are also what hm_result_slot_words reports
+    rw = np.zeros(L, dtype=np.uint32)
+    assert lib.hm_result_slot_words(ctx._h, N.HM_OP_ADD, L, wa.ctypes.data_as(u32p), wa.ctypes.data_as(u32p), rw.ctypes.data_as(u32p)) == 0
+    np.testing.assert_array_equal(rw, wo)
+    # XOR through the same call (memory-bound op, one chunk)
+    outx = np.zeros((n, 160), dtype=np.uint64)
+    assert lib.hm_apply2_host(ctx._h, N.HM_OP_XOR, n, L, wa.ctypes.data_as(u32p), ha.ctypes.data, wa.ctypes.data_as(u32p), hb.ctypes.data, outx.ctypes.data) == 0
+    np.testing.assert_array_equal(outx, ha ^ hb)
+    # requirement check happens before any work (src/context.rs:310-323)
+    ctx2 = hm.Context(hm.Parameters(64, 16, 8, 16))
+    assert lib.hm_apply2_host(ctx2._h, N.HM_OP_ADD, 1, 8, wa.ctypes.data_as(u32p), ha.ctypes.data, wa.ctypes.data_as(u32p), hb.ctypes.data, out.ctypes.data) == N.HM_ERR_OPERATION_REQUIREMENT
