@@ -261,8 +261,11 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     e2e_steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
+    e2e_step_ms = []
     for _ in range(e2e_steps):
+        ts = time.perf_counter()
         e2e_step()
+        e2e_step_ms.append((time.perf_counter() - ts) * 1e3)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -463,7 +466,7 @@ def run_ours(args, rank, local_rank, world):
                        "l2": "inputs 2 x %.0f MiB + result %.2f GiB per step >> 126 MB L2 (no flush needed)" % (n * 1280 / 2**20, n * 46912 / 2**30),
                        "sharding": "independent values split by index across ranks; no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ne * 2560, "d2h_bytes_per_step": ne * vwo * 8,
-                    "pairs_per_step": ne, "steps": e2e_steps, "call": "hm_apply2_host (pinned host ciphertexts in/out, 3-stream chunked pipeline)",
+                    "pairs_per_step": ne, "steps": e2e_steps, "step_ms": e2e_step_ms, "call": "hm_apply2_host (pinned host ciphertexts in/out, 3-stream chunked pipeline)",
                     "matches_device_result": e2e_matches},
             "gpu_launches": int(l_after - l_before),
             "kernels_in_step": ["adder_fused_kernel<8>"],

@@ -144,7 +144,7 @@ hm_batch *new_batch(hm_context *ctx, size_t n, uint32_t L, const uint64_t *degb)
 
 int alloc_batch(hm_context *ctx, hm_batch *b) {
     const size_t bytes = std::max<size_t>(b->n * b->value_words * 8, 16);
-    CK(cudaMalloc(&b->d, bytes));
+    CK(cudaMallocAsync(&b->d, bytes, ctx->stream)); // stream-ordered pool: no device-wide sync, memory is recycled
     return HM_OK;
 }
 
@@ -506,6 +506,13 @@ int hm_context_create(uint16_t d, uint16_t dp, uint16_t delta, uint16_t tau, int
         return HM_ERR_CUDA;
     }
     ctx->own_stream = true;
+    {   // keep freed blocks in the stream-ordered pool instead of returning them to the driver at every sync
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
         ctx->sm_count = prop.multiProcessorCount;
@@ -683,11 +690,11 @@ void *hm_batch_device_ptr(const hm_batch *b) { return b ? (void *)b->d : nullptr
 void hm_batch_free(hm_context *ctx, hm_batch *b) {
     if (!b) return;
     if (!ctx) ctx = b->ctx;
-    if (ctx) {
-        cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
+    if (ctx) cudaSetDevice(ctx->device);
+    if (b->d) {
+        if (ctx) cudaFreeAsync(b->d, ctx->stream); // ordered after every kernel of this context that used it
+        else cudaFree(b->d);
     }
-    if (b->d) cudaFree(b->d);
     delete b;
 }
 
@@ -971,10 +978,10 @@ int hm_encrypt(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, con
     USE_DEV(ctx);
     const size_t vbytes = n * (L / 8), mbytes = n * L * ((ctx->tau + 7u) / 8u);
     uint8_t *dv = nullptr, *dm = nullptr;
-    CK(cudaMalloc(&dv, std::max<size_t>(vbytes, 16)));
-    cudaError_t e = cudaMalloc(&dm, std::max<size_t>(mbytes, 16));
+    CK(cudaMallocAsync(&dv, std::max<size_t>(vbytes, 16), ctx->stream));
+    cudaError_t e = cudaMallocAsync(&dm, std::max<size_t>(mbytes, 16), ctx->stream);
     if (e != cudaSuccess) {
-        cudaFree(dv);
+        cudaFreeAsync(dv, ctx->stream);
         return fail_cuda(ctx, e, "cudaMalloc(masks)");
     }
     int rc = HM_OK;
@@ -984,9 +991,9 @@ int hm_encrypt(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, con
         if (e != cudaSuccess) rc = fail_cuda(ctx, e, "upload values/masks");
     }
     if (rc == HM_OK) rc = hm_encrypt_device(ctx, dv, n, L, dm, out);
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(dv);
-    cudaFree(dm);
+    cudaFreeAsync(dv, ctx->stream);
+    cudaFreeAsync(dm, ctx->stream);
+    cudaStreamSynchronize(ctx->stream); // the caller's host buffers may be reused after return
     return rc;
 }
 
@@ -1054,7 +1061,7 @@ int hm_decrypt(hm_context *ctx, const hm_batch *b, uint8_t *values_out) {
     USE_DEV(ctx);
     const size_t bytes = b->n * (b->L / 8);
     uint8_t *dout = nullptr;
-    CK(cudaMalloc(&dout, std::max<size_t>(bytes, 16)));
+    CK(cudaMallocAsync(&dout, std::max<size_t>(bytes, 16), ctx->stream));
     int rc = hm_decrypt_device(ctx, b, dout);
     if (rc == HM_OK && bytes) {
         cudaError_t e = cudaMemcpyAsync(values_out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1062,7 +1069,7 @@ int hm_decrypt(hm_context *ctx, const hm_batch *b, uint8_t *values_out) {
     }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (rc == HM_OK && e != cudaSuccess) rc = fail_cuda(ctx, e, "decrypt sync");
-    cudaFree(dout);
+    cudaFreeAsync(dout, ctx->stream);
     return rc;
 }
 
@@ -1179,7 +1186,7 @@ static int add_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
     const uint32_t NBUF = 7;
     uint64_t *arena = nullptr;
     const size_t arena_words = (size_t)NBUF * wmax;
-    CK(cudaMalloc(&arena, std::max<size_t>(n * arena_words * 8, 16)));
+    CK(cudaMallocAsync(&arena, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
     CK(cudaMemsetAsync(arena, 0, n * arena_words * 8, ctx->stream));
     auto buf = [&](uint32_t i, uint64_t degb) {
         View v;
@@ -1243,8 +1250,7 @@ static int add_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
         cur = nxt;
         dc = dt;
     }
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(arena);
+    cudaFreeAsync(arena, ctx->stream);
     return rc;
 }
 
@@ -1333,7 +1339,7 @@ static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
     CK(cudaMemGetInfo(&free_b, &total_b));
     if ((double)n * arena_words * 8.0 > 0.9 * (double)free_b) return HM_ERR_UNSUPPORTED;
     uint64_t *arena = nullptr;
-    CK(cudaMalloc(&arena, std::max<size_t>(n * arena_words * 8, 16)));
+    CK(cudaMallocAsync(&arena, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
     CK(cudaMemsetAsync(o->d, 0, n * o->value_words * 8, ctx->stream));
     auto aview = [&](const Obj &ob) {
         View v;
@@ -1380,8 +1386,7 @@ static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
             rc = launch_xor_views(ctx, rr, rr, x, n);
         }
     }
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(arena);
+    cudaFreeAsync(arena, ctx->stream);
     return rc;
 }
 
@@ -1580,6 +1585,14 @@ int hm_apply2_host(hm_context *ctx, int op, size_t n, uint32_t L, const uint32_t
         if (rc == HM_OK) rc = alloc_batch(ctx, s.a);
         if (rc == HM_OK) rc = alloc_batch(ctx, s.b);
         if (rc == HM_OK) rc = alloc_batch(ctx, s.o);
+    }
+    {   // the stage buffers were allocated in `user` stream order: the copy streams must not touch them earlier
+        cudaEvent_t ready = nullptr;
+        cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+        cudaEventRecord(ready, user);
+        cudaStreamWaitEvent(s_up, ready, 0);
+        cudaStreamWaitEvent(s_down, ready, 0);
+        cudaEventDestroy(ready);
     }
     size_t idx = 0;
     for (size_t first = 0; first < n && rc == HM_OK; first += chunk, ++idx) {
