@@ -346,6 +346,27 @@ def run_ours(args, rank, local_rank, world):
         extra["encrypt"] = {"value": n / s, "unit": "u32/s", "kernel": "encrypt_tab6_kernel", "ms": s * 1e3,
                             "hbm_GBps": n * 1792 / s / 1e9, "hbm_frac": n * 1792 / s / 1e9 / hbm_peak}
         ce.free()
+        # end-to-end encryption, host plaintexts in -> ciphertexts resident in HBM: (i) host-generated masks cross PCIe
+        # (16 B per bit), (ii) masks generated on the device from a seed (Philox4x32-10), only 4 B per u32 cross
+        hv = torch.from_numpy(a.copy()).pin_memory()
+        hm_ = torch.from_numpy(np.frombuffer(np.random.default_rng(2).bytes(n * L * 16), dtype=np.uint8).copy()).pin_memory()
+        def e2e_enc_masks():
+            o = C.c_void_p()
+            assert lib.hm_encrypt(ctx._h, hv.data_ptr(), n, L, hm_.data_ptr(), C.byref(o)) == 0
+            lib.hm_batch_free(ctx._h, o)
+        def e2e_enc_seed():
+            o = C.c_void_p()
+            assert lib.hm_encrypt_seeded(ctx._h, hv.data_ptr(), n, L, 12345, C.byref(o)) == 0
+            lib.hm_batch_free(ctx._h, o)
+        for name, fn in (("encrypt_e2e_host_masks", e2e_enc_masks), ("encrypt_e2e_seeded", e2e_enc_seed)):
+            fn(); ctx.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            ctx.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            extra[name] = {"value": n / dt, "unit": "u32/s", "ms": dt * 1e3}
+        del hv, hm_
         # gates on fresh u32 batches (gate_xor / gate_and, common.rs:5-27): n*32 bit-ciphertext pairs per launch
         xo = ctx.apply2(hm.HomomorphicXorGate, ca, cb)
         s = timed(lambda: lib.hm_apply2_into(ctx._h, N.HM_OP_XOR, ca._h, cb._h, xo._h), reps=20)

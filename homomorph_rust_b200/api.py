@@ -394,7 +394,14 @@ class Context:
     def mask_bytes(self) -> int:
         return (self._params.tau() + 7) // 8
 
-    def encrypt(self, values: np.ndarray, masks: Optional[np.ndarray] = None, rng: Optional[np.random.Generator] = None) -> Ciphered:
+    def seeded_masks(self, units: int, seed: int) -> np.ndarray:
+        """The Philox4x32-10 mask stream `encrypt(..., seed=)` uses, computed on the host (for parity checks)."""
+        out = np.zeros(units * self.mask_bytes(), dtype=np.uint8)
+        _check(self._h, N.lib().hm_masks_generate_host(self._params.tau(), units, seed, out.ctypes.data))
+        return out
+
+    def encrypt(self, values: np.ndarray, masks: Optional[np.ndarray] = None, rng: Optional[np.random.Generator] = None,
+                seed: Optional[int] = None) -> Ciphered:
         """Context::encrypt (src/context.rs:463-471) for an array of unsigned/signed integers.
 
         ``masks``: (n, L, ceil(tau/8)) uint8, the subset U of every bit (src/cipher.rs:92-97,106);
@@ -408,6 +415,12 @@ class Context:
         le = values.astype(values.dtype.newbyteorder("<"), copy=False)
         n, L = values.size, values.dtype.itemsize * 8
         raw = np.frombuffer(le.tobytes(), dtype=np.uint8)
+        if seed is not None:  # masks generated on the device from a counter-based PRNG; nothing but plaintext is uploaded
+            out = C.c_void_p()
+            _check(self._h, N.lib().hm_encrypt_seeded(self._h, raw.ctypes.data, n, L, seed, C.byref(out)))
+            c = Ciphered(self, out.value)
+            c.dtype = values.dtype
+            return c
         if masks is None:
             masks = np.frombuffer(_rng_bytes(rng, n * L * self.mask_bytes()), dtype=np.uint8)
         masks = np.ascontiguousarray(masks, dtype=np.uint8).reshape(-1)

@@ -997,6 +997,57 @@ int hm_encrypt(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, con
     return rc;
 }
 
+// ---- seeded subset masks (Philox4x32-10) -----------------------------------------------------------
+int hm_masks_generate_host(uint16_t tau, size_t units, uint64_t seed, uint8_t *masks_out) {
+    if (!masks_out || tau == 0) return HM_ERR_INVALID_ARGUMENT;
+    const uint32_t mb = (tau + 7u) / 8u, blocks = (mb + 15) / 16;
+    for (size_t u = 0; u < units; ++u)
+        for (uint32_t b = 0; b < blocks; ++b) {
+            uint32_t r[4];
+            hmk::philox4x32_10((uint32_t)u, (uint32_t)((uint64_t)u >> 32), b, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+            const uint32_t nb = std::min<uint32_t>(16, mb - 16 * b);
+            for (uint32_t q = 0; q < nb; ++q) masks_out[u * mb + 16 * b + q] = (uint8_t)(r[q >> 2] >> (8 * (q & 3)));
+        }
+    return HM_OK;
+}
+
+int hm_masks_generate_device(hm_context *ctx, size_t units, uint64_t seed, uint8_t *d_masks_out) {
+    if (!ctx || (!d_masks_out && units)) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    if (!units) return HM_OK;
+    const uint32_t mb = (ctx->tau + 7u) / 8u;
+    const int grid = grid_for(ctx, (uint64_t)units * ((mb + 15) / 16), 256, 16);
+    hmk::mask_fill_kernel<<<grid, 256, 0, ctx->stream>>>(d_masks_out, units, mb, seed);
+    LAUNCHED("mask_fill_kernel");
+    return HM_OK;
+}
+
+int hm_encrypt_seeded(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, uint64_t seed, hm_batch **out) {
+    if (!ctx || !out || (!values && n)) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_pk) return HM_ERR_PUBLIC_KEY_UNSET;
+    if (L == 0 || L % 8 != 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    const size_t vbytes = n * (L / 8), mbytes = n * L * ((ctx->tau + 7u) / 8u);
+    uint8_t *dv = nullptr, *dm = nullptr;
+    CK(cudaMallocAsync(&dv, std::max<size_t>(vbytes, 16), ctx->stream));
+    cudaError_t e = cudaMallocAsync(&dm, std::max<size_t>(mbytes, 16), ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(dv, ctx->stream);
+        return fail_cuda(ctx, e, "cudaMalloc(masks)");
+    }
+    int rc = HM_OK;
+    if (n) {
+        e = cudaMemcpyAsync(dv, values, vbytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = fail_cuda(ctx, e, "upload values");
+    }
+    if (rc == HM_OK) rc = hm_masks_generate_device(ctx, n * L, seed, dm);
+    if (rc == HM_OK) rc = hm_encrypt_device(ctx, dv, n, L, dm, out);
+    cudaFreeAsync(dv, ctx->stream);
+    cudaFreeAsync(dm, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+
 int hm_decrypt_device(hm_context *ctx, const hm_batch *b, uint8_t *d_values_out) {
     if (!ctx || !b || (!d_values_out && b->n)) return HM_ERR_INVALID_ARGUMENT;
     if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;       // context.rs:480-488

@@ -98,6 +98,44 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------
+// Subset masks on the device: the reference draws tau.div_ceil(8) bytes per bit from getrandom
+// (src/cipher.rs:92-97); here they can instead come from Philox4x32-10 (Random123), a counter-based generator, so
+// the same stream is reproducible on the host for parity checks and no mask crosses PCIe.
+//   bytes [16 b, 16 b + 16) of the mask of bit-ciphertext u = Philox(counter = (u_lo, u_hi, b, 0), key = seed)
+// ----------------------------------------------------------------------------------------
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static __global__ void __launch_bounds__(256) mask_fill_kernel(uint8_t *__restrict__ masks, uint64_t units, uint32_t mask_bytes,
+                                                               uint64_t seed) {
+    const uint32_t blocks = (mask_bytes + 15) / 16;
+    const uint64_t total = units * blocks;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t u = i / blocks;
+        const uint32_t b = (uint32_t)(i % blocks);
+        uint32_t r[4];
+        philox4x32_10((uint32_t)u, (uint32_t)(u >> 32), b, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        uint8_t *dst = masks + u * mask_bytes + 16ull * b;
+        const uint32_t nb = (mask_bytes - 16 * b < 16) ? (mask_bytes - 16 * b) : 16;
+        if (nb == 16 && (mask_bytes % 16) == 0) {
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
+        } else {
+            for (uint32_t q = 0; q < nb; ++q) dst[q] = (uint8_t)(r[q >> 2] >> (8 * (q & 3)));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // K2  subset-XOR encryption                         reference src/cipher.rs:99-115
 //
 //   C = XOR_{i : mask bit i} T_i  XOR  x

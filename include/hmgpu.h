@@ -149,6 +149,14 @@ int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32
 /* Same, writing into an existing batch of n values x L fresh-width slots (no allocation). */
 int hm_encrypt_device_into(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
                            hm_batch *out);
+/* Seeded subset masks (Philox4x32-10, Random123): bytes [16 b, 16 b + 16) of the mask of bit-ciphertext u are
+ * Philox(counter = (u_lo, u_hi, b, 0), key = (seed_lo, seed_hi)), words little endian, truncated to ceil(tau/8) bytes.
+ * The *_host variant computes the same stream on the CPU (no GPU needed), so a seeded encryption can be reproduced
+ * bit for bit by the reference/oracle fed with these masks.  hm_encrypt_seeded = hm_encrypt with device-generated
+ * masks: only the plaintext crosses PCIe. */
+int hm_masks_generate_host(uint16_t tau, size_t units, uint64_t seed, uint8_t *masks_out);
+int hm_masks_generate_device(hm_context *ctx, size_t units, uint64_t seed, uint8_t *d_masks_out);
+int hm_encrypt_seeded(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, uint64_t seed, hm_batch **out);
 /* Context::decrypt -> Ciphered::try_decipher -> CipheredBit::decipher — src/context.rs:480-488,
  * src/cipher.rs:217-250, :119-122.  Writes n * (L/8) bytes.  L % 8 != 0 -> HM_ERR_INVALID_LENGTH. */
 int hm_decrypt(hm_context *ctx, const hm_batch *b, uint8_t *values_out);

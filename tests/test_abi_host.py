@@ -100,3 +100,32 @@ def test_host_keygen_matches_oracle(oracle, params):
     # key byte round trips, src/context.rs:616-635
     assert hm.SecretKey.from_bytes(sk.to_bytes()).to_bytes() == sk.to_bytes()
     assert hm.PublicKey.from_bytes(pk.to_bytes()).to_bytes() == pk.to_bytes()
+
+
+def test_philox_mask_stream_host():
+    """hm_masks_generate_host: Philox4x32-10 known answers (Random123 kat_vectors) and the documented stream layout."""
+    lib = hm.lib()
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+
+    def philox(c, k):
+        c, k = list(c), list(k)
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+            k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+        return c
+
+    assert philox([0] * 4, [0] * 2) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    for tau, units, seed in [(128, 5, 0), (256, 3, 0x1234_5678_9ABC_DEF0), (5, 9, 7), (200, 4, 2**64 - 1)]:
+        mb = (tau + 7) // 8
+        out = np.zeros(units * mb, dtype=np.uint8)
+        assert lib.hm_masks_generate_host(tau, units, seed, out.ctypes.data) == 0
+        want = bytearray()
+        for u in range(units):
+            row = bytearray()
+            for b in range((mb + 15) // 16):
+                for w in philox([u & 0xFFFFFFFF, u >> 32, b, 0], [seed & 0xFFFFFFFF, seed >> 32]):
+                    row += int(w).to_bytes(4, "little")
+            want += row[:mb]
+        assert out.tobytes() == bytes(want)

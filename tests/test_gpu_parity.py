@@ -381,3 +381,23 @@ def test_apply2_host_pipeline(oracle, hm):
     # requirement check happens before any work (src/context.rs:310-323)
     ctx2 = hm.Context(hm.Parameters(64, 16, 8, 16))
     assert lib.hm_apply2_host(ctx2._h, N.HM_OP_ADD, 1, 8, wa.ctypes.data_as(u32p), ha.ctypes.data, wa.ctypes.data_as(u32p), hb.ctypes.data, out.ctypes.data) == N.HM_ERR_OPERATION_REQUIREMENT
+
+
+@pytest.mark.parametrize("params,dtype,n", [(CONFIG_A, np.uint32, 300), (CONFIG_B, np.uint8, 40), ((6, 3, 2, 5), np.uint8, 11), ((64, 32, 8, 200), np.uint16, 7)])
+def test_encrypt_seeded_device_masks(oracle, hm, params, dtype, n):
+    """Masks generated on the device (Philox4x32-10) == the documented host stream, and the resulting ciphertexts ==
+    the oracle fed with that stream (so a seeded run is reproducible by the reference with a getrandom shim)."""
+    rng = np.random.default_rng(n)
+    sk, pk, ctx = setup(oracle, hm, params, 77)
+    L = np.dtype(dtype).itemsize * 8
+    values = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    seed = 0xC0FFEE_0000_0001 + n
+    ct = ctx.encrypt(values, seed=seed)
+    masks = ctx.seeded_masks(n * L, seed)
+    want = oracle_encrypt(oracle, pk, values, masks)
+    np.testing.assert_array_equal(ct.to_host(), expected_padded(want, n, ct.slot_words()))
+    # same seed, explicit host masks: identical batch
+    np.testing.assert_array_equal(ctx.encrypt(values, masks).to_host(), ct.to_host())
+    assert not np.array_equal(ctx.encrypt(values, seed=seed + 1).to_host(), ct.to_host())
+    if params[2] * 2 <= params[0]:
+        np.testing.assert_array_equal(ctx.decrypt(ct), values)
