@@ -40,6 +40,7 @@ struct hm_batch {
     std::vector<uint64_t> degb; // per-slot degree bound (>= true degree of every polynomial in the slot)
     size_t value_words = 0;
     uint64_t *d = nullptr;
+    bool pooled = false; // allocated from the stream-ordered pool (else plain cudaMalloc)
 };
 
 struct hm_context {
@@ -144,7 +145,15 @@ hm_batch *new_batch(hm_context *ctx, size_t n, uint32_t L, const uint64_t *degb)
 
 int alloc_batch(hm_context *ctx, hm_batch *b) {
     const size_t bytes = std::max<size_t>(b->n * b->value_words * 8, 16);
-    CK(cudaMallocAsync(&b->d, bytes, ctx->stream)); // stream-ordered pool: no device-wide sync, memory is recycled
+    // Stream-ordered pool for ordinary batches (no device-wide sync, blocks are recycled).  Multi-GB results go through
+    // plain cudaMalloc: returning such a block to the pool costs ~0.5 s of unmapping at the next synchronisation.
+    if (bytes <= ((size_t)1 << 30)) {
+        CK(cudaMallocAsync(&b->d, bytes, ctx->stream));
+        b->pooled = true;
+    } else {
+        CK(cudaMalloc(&b->d, bytes));
+        b->pooled = false;
+    }
     return HM_OK;
 }
 
@@ -692,8 +701,12 @@ void hm_batch_free(hm_context *ctx, hm_batch *b) {
     if (!ctx) ctx = b->ctx;
     if (ctx) cudaSetDevice(ctx->device);
     if (b->d) {
-        if (ctx) cudaFreeAsync(b->d, ctx->stream); // ordered after every kernel of this context that used it
-        else cudaFree(b->d);
+        if (ctx && b->pooled) {
+            cudaFreeAsync(b->d, ctx->stream); // ordered after every kernel of this context that used it
+        } else {
+            if (ctx) cudaStreamSynchronize(ctx->stream);
+            cudaFree(b->d);
+        }
     }
     delete b;
 }
@@ -1739,6 +1752,13 @@ static int mulrem_fresh_exec(hm_context *ctx, const hm_batch *a, const hm_batch 
         auto kern = hmk::mulrem_fresh_kernel<WD, WS, 2, TH, 1>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid_for(ctx, pairs, TH, 4), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
+    } else if (mode == 3 || mode == 4 || mode == 5) { // occupancy experiments
+        constexpr int TH = 128;
+        const size_t smem = (size_t)4 * 256 * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;
+        auto kern = mode == 3 ? hmk::mulrem_fresh_kernel<WD, WS, 2, TH, 1, 5>
+                              : (mode == 4 ? hmk::mulrem_fresh_kernel<WD, WS, 2, TH, 1, 3> : hmk::mulrem_fresh_kernel<WD, WS, 2, TH, 1, 6>);
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid_for(ctx, pairs, TH, mode == 3 ? 5 : (mode == 4 ? 3 : 6)), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
     } else { // Karatsuba on the multiplier, one 512-thread CTA per SM, 8-way replicated (conflict-free) fold tables
         constexpr int TH = 512, REP = 8;
         const size_t smem = (size_t)4 * 256 * REP * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;

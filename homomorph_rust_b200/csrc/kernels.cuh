@@ -1002,8 +1002,8 @@ static __global__ void __launch_bounds__(MUL_WARPS * 32) rem_generic_kernel(View
 //   Operand tiles are staged in shared memory by TMA (two buffers); the 2D+1-bit product stays
 //   in registers and is folded down to d bits with the tables above; only d bits are written.
 // ----------------------------------------------------------------------------------------
-template <int WD, int WS, int MODE, int MR_THREADS, int REP>
-__global__ void __launch_bounds__(MR_THREADS, WD >= 32 ? 2 : (MR_THREADS >= 512 ? 1 : 4)) mulrem_fresh_kernel(const uint64_t *__restrict__ A,
+template <int WD, int WS, int MODE, int MR_THREADS, int REP, int MINB = (WD >= 32 ? 2 : (MR_THREADS >= 512 ? 1 : 4))>
+__global__ void __launch_bounds__(MR_THREADS, MINB) mulrem_fresh_kernel(const uint64_t *__restrict__ A,
                                                                   const uint64_t *__restrict__ B,
                                                                   uint64_t *__restrict__ O, uint64_t n,
                                                                   const uint32_t *__restrict__ Tg) {

@@ -26,3 +26,12 @@ def encdev():
 T("encrypt_device(alloc+kernel+free)", encdev)
 ce = ctx.encrypt(a[:n], seed=1)
 T("encrypt_device_into", lambda: lib.hm_encrypt_device_into(ctx._h, dv.data_ptr(), n, L, dm.data_ptr(), ce._h))
+hmk = torch.from_numpy(np.frombuffer(np.random.default_rng(2).bytes(n * L * 16), dtype=np.uint8).copy()).pin_memory()
+def hostmasks():
+    o = C.c_void_p(); assert lib.hm_encrypt(ctx._h, hv.data_ptr(), n, L, hmk.data_ptr(), C.byref(o)) == 0; lib.hm_batch_free(ctx._h, o)
+T("encrypt(host masks, pinned)", hostmasks, reps=8)
+big = ctx.encrypt(a, seed=3)
+s = ctx.apply2(hm.HomomorphicAddition, big, big)   # 12 GB result, then freed: does the pool still behave?
+s.free()
+T("encrypt(host masks) after a 12 GB alloc/free", hostmasks, reps=8)
+T("encrypt_seeded after", seeded, reps=5)
