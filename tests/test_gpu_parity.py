@@ -401,3 +401,46 @@ def test_encrypt_seeded_device_masks(oracle, hm, params, dtype, n):
     assert not np.array_equal(ctx.encrypt(values, seed=seed + 1).to_host(), ct.to_host())
     if params[2] * 2 <= params[0]:
         np.testing.assert_array_equal(ctx.decrypt(ct), values)
+
+
+def test_poly_mul_random_shapes(oracle, hm):
+    """Randomised widths and degree bounds through every multiply kernel class (thread-per-product Karatsuba for the
+    'k*256 + 1 bit' shapes, warp-cooperative tiles + scalar tail for the rest) against Polynomial::mul of the oracle."""
+    rng = np.random.default_rng(2026)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 2)
+    shapes = [(256, 256), (512, 512), (512, 1024), (1024, 512), (1024, 1024), (256, 512), (2048, 1024)]
+    for _ in range(25):
+        shapes.append((int(rng.integers(0, 3000)), int(rng.integers(0, 3000))))
+    shapes += [(0, 0), (0, 700), (63, 64), (64, 63), (4095, 1), (23552, 768), (768, 23552), (14336, 8192)]
+    for da, db in shapes:
+        n = 7
+        wa, wb = da // 64 + 1, db // 64 + 1
+        A = random_polys(rng, n, wa, (da % 64) + 1)
+        B = random_polys(rng, n, wb, (db % 64) + 1)
+        A[:, -1] |= np.uint64(1) << np.uint64(da % 64)  # exact degree da for most rows
+        A[0] = 0
+        B[1] = 0
+        ba = ctx.upload(A, [wa], [da])
+        bb = ctx.upload(B, [wb], [db])
+        prod = ctx.poly_mul(ba, bb)
+        assert list(prod.slot_words()) == [(da + db) // 64 + 1]  # out len, src/polynomial.rs:264
+        want = oracle.poly_binop(oracle.POLY_MUL, oracle.PolyVec.from_padded(A), oracle.PolyVec.from_padded(B))
+        np.testing.assert_array_equal(prod.to_host(), expected_padded(want, n, prod.slot_words()), err_msg=f"da={da} db={db}")
+        if da + db >= 128:
+            rem = ctx.poly_rem(prod)
+            wantr = oracle.poly_binop(oracle.POLY_REM, want, sk)
+            np.testing.assert_array_equal(rem.to_host(), expected_padded(wantr, n, rem.slot_words()), err_msg=f"rem da={da} db={db}")
+
+
+def test_empty_batches(oracle, hm):
+    """n = 0 everywhere (the reference's Vec-based API accepts empty inputs)."""
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 2)
+    e = ctx.encrypt(np.zeros(0, dtype=np.uint8))
+    assert len(e) == 0
+    for op in (hm.HomomorphicXorGate, hm.HomomorphicAndGate, hm.HomomorphicOrGate, hm.HomomorphicAddition, hm.HomomorphicMultiplication):
+        r = ctx.apply2(op, e, e)
+        assert len(r) == 0 and r.bits == 8
+        assert ctx.decrypt(r).size == 0
+    ctx.apply1(hm.HomomorphicNotGate, e)
+    assert len(ctx.poly_mulrem(e, e)) == 0
+    assert hm.Ciphered.from_bytes(ctx, e.to_bytes()).bits == 8
