@@ -1454,16 +1454,20 @@ static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
     return rc;
 }
 
-static bool adder_fast_path_ok(const hm_context *ctx, const hm_batch *a, const hm_batch *b, size_t *smem_per_warp) {
-    if (!ctx->has_pk) return false;
+// The fused ripple-carry kernel is instantiated for D = d+d' in {128, 256} (WD = D/32 = 4, 8; its multiplier mask must fit
+// 32 bits, i.e. 3 WD + 1 <= 32) and needs both operands fresh (every slot with degree bound D).  Anything else goes
+// through the generic view-based circuit.
+static int adder_fast_path_wd(const hm_context *ctx, const hm_batch *a, const hm_batch *b, size_t *smem_per_warp) {
+    if (!ctx->has_pk) return 0;
     const uint64_t D = ctx->fresh_deg;
-    if (D != 256) return false; // tuned instantiation: D = 32*8 (config A family)
+    if (D != 128 && D != 256) return 0;
     for (uint32_t k = 0; k < a->L; ++k)
-        if (a->degb[k] != D || b->degb[k] != D) return false;
-    if (a->L < 2) return false;
-    const size_t words = hmk::AdderCfg<8>::warp_words(a->L);
+        if (a->degb[k] != D || b->degb[k] != D) return 0;
+    if (a->L < 2) return 0;
+    const int wd = (int)(D / 32);
+    const size_t words = wd == 4 ? hmk::AdderCfg<4>::warp_words(a->L) : hmk::AdderCfg<8>::warp_words(a->L);
     *smem_per_warp = words * 4;
-    return words * 4 <= ctx->smem_optin;
+    return words * 4 <= ctx->smem_optin ? wd : 0;
 }
 
 // runs `op` into the already allocated result batch o (layout = result_bounds of the operands)
@@ -1507,15 +1511,14 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
         }
         case HM_OP_ADD: {
             size_t per_warp = 0;
-            if (!force_generic && adder_fast_path_ok(ctx, a, b, &per_warp)) {
+            const int wd = force_generic ? 0 : adder_fast_path_wd(ctx, a, b, &per_warp);
+            if (wd) {
                 int warps = (int)std::min<size_t>(4, ctx->smem_optin / per_warp);
                 if (warps < 1) warps = 1;
                 const size_t smem = per_warp * warps;
                 static const int mode = getenv("HM_ADDER_MODE") ? atoi(getenv("HM_ADDER_MODE")) : 1;
-                static const int ts = getenv("HM_ADDER_TS") ? atoi(getenv("HM_ADDER_TS")) : 0;
-                auto kern = mode == 0 ? hmk::adder_fused_kernel<8, 0, 0>
-                                      : (ts == 1 ? hmk::adder_fused_kernel<8, 1, 1>
-                                                 : (ts == 2 ? hmk::adder_fused_kernel<8, 1, 2> : hmk::adder_fused_kernel<8, 1, 0>));
+                auto kern = wd == 4 ? hmk::adder_fused_kernel<4, 1, 0>
+                                    : (mode == 0 ? hmk::adder_fused_kernel<8, 0, 0> : hmk::adder_fused_kernel<8, 1, 0>);
                 CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 const unsigned grid = (unsigned)((n + warps - 1) / warps);
                 kern<<<grid, warps * 32, smem, ctx->stream>>>(a->d, b->d, o->d, n, a->L, make_layout(o));
@@ -1752,13 +1755,6 @@ static int mulrem_fresh_exec(hm_context *ctx, const hm_batch *a, const hm_batch 
         auto kern = hmk::mulrem_fresh_kernel<WD, WS, 2, TH, 1>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid_for(ctx, pairs, TH, 4), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
-    } else if (mode == 3 || mode == 4 || mode == 5) { // occupancy experiments
-        constexpr int TH = 128;
-        const size_t smem = (size_t)4 * 256 * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;
-        auto kern = mode == 3 ? hmk::mulrem_fresh_kernel<WD, WS, 2, TH, 1, 5>
-                              : (mode == 4 ? hmk::mulrem_fresh_kernel<WD, WS, 2, TH, 1, 3> : hmk::mulrem_fresh_kernel<WD, WS, 2, TH, 1, 6>);
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid_for(ctx, pairs, TH, mode == 3 ? 5 : (mode == 4 ? 3 : 6)), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
     } else { // Karatsuba on the multiplier, one 512-thread CTA per SM, 8-way replicated (conflict-free) fold tables
         constexpr int TH = 512, REP = 8;
         const size_t smem = (size_t)4 * 256 * REP * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;

@@ -444,3 +444,26 @@ def test_empty_batches(oracle, hm):
     ctx.apply1(hm.HomomorphicNotGate, e)
     assert len(ctx.poly_mulrem(e, e)) == 0
     assert hm.Ciphered.from_bytes(ctx, e.to_bytes()).bits == 8
+
+
+@pytest.mark.parametrize("params,dtype,n", [((64, 64, 1, 32), np.uint8, 20), ((64, 64, 1, 32), np.uint32, 5), ((256, 256, 1, 64), np.uint8, 9), ((256, 256, 1, 64), np.uint16, 4)])
+def test_add_fused_other_degrees(oracle, hm, params, dtype, n):
+    """The fused ripple-carry kernel at D = d+d' = 128 (instantiation WD = 4) and the generic circuit at D = 512, against
+    the oracle and against each other."""
+    rng = np.random.default_rng(n + params[0])
+    sk, pk, ctx = setup(oracle, hm, params, 91)
+    L = np.dtype(dtype).itemsize * 8
+    a = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    b = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    ma, mb = masks_for(rng, n, L, params[3]), masks_for(rng, n, L, params[3])
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    r = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+    oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
+    want, _ = oracle.apply(oracle.OP_ADD, oa, ob, L, threads=oracle.max_threads())
+    D = params[0] + params[1]
+    assert list(r.slot_words()) == [D // 64 + 1] + [((3 * k - 1) * D) // 64 + 1 for k in range(1, L)]
+    got = r.to_host()
+    np.testing.assert_array_equal(got, expected_padded(want, n, r.slot_words()))
+    np.testing.assert_array_equal(ctx.apply2(hm.HomomorphicAddition, ca, cb, generic=True).to_host(), got)
+    od, _ = oracle.decrypt(sk, want, L)
+    np.testing.assert_array_equal(ctx.decrypt(r).view(np.uint8), od)
