@@ -1516,7 +1516,20 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                 int warps = (int)std::min<size_t>(4, ctx->smem_optin / per_warp);
                 if (warps < 1) warps = 1;
                 const size_t smem = per_warp * warps;
-                static const int mode = getenv("HM_ADDER_MODE") ? atoi(getenv("HM_ADDER_MODE")) : 1;
+                // HM_ADDER_MODE: 0 / 1 = warp-per-value comb kernel (pair / single uniform branches), m >= 3 = thread-per-value
+                // Karatsuba kernel with m-1 CTAs per SM (default: 4 CTAs of 128 threads, 128 registers)
+                static const int mode = getenv("HM_ADDER_MODE") ? atoi(getenv("HM_ADDER_MODE")) : 5;
+                if (mode >= 3 && wd == 8 && a->L <= 32) { // thread-per-value Karatsuba chain; mode - 1 = CTAs per SM
+                    const int per_sm = mode - 1;
+                    const int blocks = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->sm_count * per_sm);
+                    uint32_t *scratch = nullptr;
+                    CK(cudaMallocAsync(&scratch, (size_t)blocks * 128 * hmk::ADT_THREAD_WORDS * 4, ctx->stream));
+                    auto tk = per_sm == 2 ? hmk::adder_thread_kernel<2> : (per_sm == 3 ? hmk::adder_thread_kernel<3> : (per_sm == 4 ? hmk::adder_thread_kernel<4> : (per_sm == 5 ? hmk::adder_thread_kernel<5> : (per_sm == 6 ? hmk::adder_thread_kernel<6> : hmk::adder_thread_kernel<8>))));
+                    tk<<<blocks, 128, 0, ctx->stream>>>(a->d, b->d, o->d, n, a->L, make_layout(o), scratch);
+                    rc = post_launch(ctx, "adder_thread_kernel");
+                    cudaFreeAsync(scratch, ctx->stream);
+                    break;
+                }
                 auto kern = wd == 4 ? hmk::adder_fused_kernel<4, 1, 0>
                                     : (mode == 0 ? hmk::adder_fused_kernel<8, 0, 0> : hmk::adder_fused_kernel<8, 1, 0>);
                 CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1338,6 +1338,211 @@ __global__ void __launch_bounds__(128, 5) adder_fused_kernel(const uint64_t *__r
 }
 
 // ----------------------------------------------------------------------------------------
+// K6b  ripple-carry adder, one THREAD per value (D = 256): the chain c_{k+1} = m_k c_k + g_k evaluated with
+// Karatsuba on the integer multiplier instead of the warp-uniform comb.  c_k is cut into 24-word chunks; every chunk
+// times the 24 low words of m_k is a 3-way Karatsuba of six 8x8-word products (clmul_kara<8>: 27 single-word leaves
+// each, 16 IMAD.WIDE + 20 LOP3 per leaf), accumulated into a 48-word register window whose upper half is the carry
+// into the next chunk.  The carry polynomials live in a per-thread scratch row in HBM/L2 (two buffers); s_{k+1} is
+// written while c_{k+1} is produced.  No warp cooperation, no shared memory, no idle lanes in the short early steps.
+// ----------------------------------------------------------------------------------------
+template <int O> __device__ __forceinline__ void xor16_at(uint32_t (&t)[48], const uint32_t (&r)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[O + i] ^= r[i];
+}
+
+// t ^= m * c for 24-word m and c (3-way Karatsuba over 8-word blocks: 6 block products).  m and c are read from
+// memory (per-thread scratch, L1 hits) block by block so that only the 48-word accumulator stays live, and the six
+// products share ONE copy of the 8x8-word Karatsuba code (rolled loop): the kernel is instruction-fetch sensitive.
+__device__ __forceinline__ void mul24_acc(const uint32_t *__restrict__ m, const uint32_t *__restrict__ c, uint32_t (&t)[48]) {
+    auto blk = [](uint32_t (&dst)[8], const uint32_t *src) {
+        const uint4 lo = *reinterpret_cast<const uint4 *>(src), hi = *reinterpret_cast<const uint4 *>(src + 4);
+        dst[0] = lo.x; dst[1] = lo.y; dst[2] = lo.z; dst[3] = lo.w;
+        dst[4] = hi.x; dst[5] = hi.y; dst[6] = hi.z; dst[7] = hi.w;
+    };
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+        // i: 0 -> P0 = m0 c0, 1 -> P1 = m1 c1, 2 -> P2 = m2 c2, 3 -> (m0+m1)(c0+c1), 4 -> (m0+m2)(c0+c2), 5 -> (m1+m2)(c1+c2)
+        const int o1 = (i < 3) ? 8 * i : (i == 5 ? 8 : 0);
+        const int o2 = (i < 3) ? -1 : (i == 3 ? 8 : 16);
+        uint32_t x[8], y[8], r[16];
+        blk(x, m + o1);
+        blk(y, c + o1);
+        if (o2 >= 0) {
+            uint32_t u[8], w[8];
+            blk(u, m + o2);
+            blk(w, c + o2);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                x[q] ^= u[q];
+                y[q] ^= w[q];
+            }
+        }
+        clmul_kara<8>(x, y, r);
+        switch (i) {
+            case 0: xor16_at<0>(t, r); xor16_at<8>(t, r); xor16_at<16>(t, r); break;   // P0 at 0, cross terms at 8, 16
+            case 1: xor16_at<16>(t, r); xor16_at<8>(t, r); xor16_at<24>(t, r); break;  // P1 at 16, cross terms at 8, 24
+            case 2: xor16_at<32>(t, r); xor16_at<16>(t, r); xor16_at<24>(t, r); break; // P2 at 32, cross terms at 16, 24
+            case 3: xor16_at<8>(t, r); break;
+            case 4: xor16_at<16>(t, r); break;
+            default: xor16_at<24>(t, r); break;
+        }
+    }
+}
+
+// out-of-line 8x8-word product for the once-per-bit quantities (g_k, m_k): keeps their three uses from tripling the code
+static __device__ __noinline__ void kara8_call(const uint32_t *x, const uint32_t *y, uint32_t *r) {
+    uint32_t a[8], b[8], o[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = x[i];
+        b[i] = y[i];
+    }
+    clmul_kara<8>(a, b, o);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = o[i];
+}
+
+constexpr int ADT_ROW = 768;                 // words per carry buffer row (>= 737 + one chunk of slack, multiple of 24)
+constexpr int ADT_THREAD_WORDS = 2 * ADT_ROW + 32; // two carry buffers + m_k
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) adder_thread_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
+                                                              uint64_t *__restrict__ O, uint64_t n, uint32_t L, Layout lo,
+                                                              uint32_t *__restrict__ scratch) {
+    constexpr int WD = 8, WF = 5;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t *buf0 = scratch + tid * ADT_THREAD_WORDS, *buf1 = buf0 + ADT_ROW, *mbuf = buf1 + ADT_ROW;
+    for (uint64_t v = tid; v < n; v += nthreads) {
+        const uint64_t *Av = A + v * (uint64_t)L * WF, *Bv = B + v * (uint64_t)L * WF;
+        uint32_t *Ov = reinterpret_cast<uint32_t *>(O + v * (uint64_t)lo.value_words);
+        uint32_t *ccur = buf0, *cnxt = buf1;
+        uint32_t len = 0; // words of c_k currently valid in ccur (c_0 = 0)
+        for (uint32_t k = 0; k < L; ++k) {
+            // ---- per-bit quantities: p = a + b, g = a * b, m = (1 + g) * p -----------------------------------------
+            uint32_t a[WD], b[WD], p[WD];
+#pragma unroll
+            for (int j = 0; j < WD / 2; ++j) {
+                const uint64_t x = __ldg(Av + (size_t)k * WF + j), y = __ldg(Bv + (size_t)k * WF + j);
+                a[2 * j] = (uint32_t)x; a[2 * j + 1] = (uint32_t)(x >> 32);
+                b[2 * j] = (uint32_t)y; b[2 * j + 1] = (uint32_t)(y >> 32);
+            }
+            const uint32_t atop = (uint32_t)__ldg(Av + (size_t)k * WF + WD / 2) & 1u, btop = (uint32_t)__ldg(Bv + (size_t)k * WF + WD / 2) & 1u;
+#pragma unroll
+            for (int j = 0; j < WD; ++j) p[j] = a[j] ^ b[j];
+            const uint32_t ptop = atop ^ btop;
+            // ---- s_k = p_k + c_k (k = 0: c = 0) --------------------------------------------------------------------
+            {
+                uint32_t *dst = Ov + 2 * lo.off[k];
+                const uint32_t wo = 2 * (lo.off[k + 1] - lo.off[k]);
+                if (k == 0) {
+#pragma unroll
+                    for (int j = 0; j < WD; ++j) dst[j] = p[j];
+                    dst[WD] = ptop;
+                    for (uint32_t j = WD + 1; j < wo; ++j) dst[j] = 0;
+                }
+                // for k >= 1 the slot was written while c_k was produced (see below)
+            }
+            if (k + 1 == L) break;
+            uint32_t g[2 * WD];
+            kara8_call(a, b, g);
+            const uint32_t ma = 0u - atop, mb = 0u - btop;
+#pragma unroll
+            for (int j = 0; j < WD; ++j) g[WD + j] ^= (b[j] & ma) ^ (a[j] & mb);
+            const uint32_t gtop = atop & btop;
+            // next bit's p (to emit s_{k+1} on the fly)
+            uint32_t pn[WD + 1];
+#pragma unroll
+            for (int j = 0; j < WD / 2; ++j) {
+                const uint64_t x = __ldg(Av + (size_t)(k + 1) * WF + j) ^ __ldg(Bv + (size_t)(k + 1) * WF + j);
+                pn[2 * j] = (uint32_t)x; pn[2 * j + 1] = (uint32_t)(x >> 32);
+            }
+            pn[WD] = (uint32_t)(__ldg(Av + (size_t)(k + 1) * WF + WD / 2) ^ __ldg(Bv + (size_t)(k + 1) * WF + WD / 2)) & 1u;
+            uint32_t *sdst = Ov + 2 * lo.off[k + 1];
+            const uint32_t swo = 2 * (lo.off[k + 2] - lo.off[k + 1]);
+            if (k == 0) { // c_1 = g_0
+#pragma unroll
+                for (int j = 0; j < 2 * WD; ++j) {
+                    ccur[j] = g[j];
+                    sdst[j] = g[j] ^ (j <= WD ? pn[j] : 0u);
+                }
+                ccur[2 * WD] = gtop;
+                sdst[2 * WD] = gtop;
+                for (uint32_t j = 2 * WD + 1; j < swo; ++j) sdst[j] = 0;
+                for (uint32_t j = 2 * WD + 1; j < 24; ++j) ccur[j] = 0;
+                len = 2 * WD + 1;
+                continue;
+            }
+            // m = p + g * p : 24 low words + the coefficient of X^768
+            uint32_t m[24];
+            {
+                uint32_t glo[WD], ghi[WD], q0[2 * WD], q1[2 * WD];
+#pragma unroll
+                for (int j = 0; j < WD; ++j) { glo[j] = g[j]; ghi[j] = g[WD + j]; }
+                kara8_call(glo, p, q0);
+                kara8_call(ghi, p, q1);
+#pragma unroll
+                for (int j = 0; j < WD; ++j) {
+                    m[j] = q0[j] ^ p[j];
+                    m[WD + j] = q0[WD + j] ^ q1[j];
+                    m[2 * WD + j] = q1[WD + j];
+                }
+                const uint32_t mp = 0u - ptop, mg = 0u - gtop;
+#pragma unroll
+                for (int j = 0; j < 2 * WD; ++j) m[WD + j] ^= g[j] & mp;
+#pragma unroll
+                for (int j = 0; j < WD; ++j) m[2 * WD + j] ^= p[j] & mg;
+                m[WD] ^= ptop;
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) reinterpret_cast<uint4 *>(mbuf)[q] = make_uint4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+            const uint32_t mtop = gtop & ptop;
+            // ---- c_{k+1} = m c_k + g_k, chunk by chunk; t[0..24) carries the upper half of the previous chunk ---------
+            uint32_t t[48];
+#pragma unroll
+            for (int i = 0; i < 48; ++i) t[i] = 0;
+            const uint32_t nchunks = (len + 23) / 24;
+            for (uint32_t j = 0; j <= nchunks; ++j) {
+                if (j < nchunks) mul24_acc(mbuf, ccur + 24 * j, t);
+                if (mtop && j >= 1) { // X^768 * c: chunk j-1 lands in chunk j
+                    const uint32_t *prev = ccur + 24 * (j - 1);
+#pragma unroll
+                    for (int i = 0; i < 24; ++i) t[i] ^= prev[i];
+                }
+                if (j == 0) {
+#pragma unroll
+                    for (int i = 0; i < 2 * WD; ++i) t[i] ^= g[i];
+                    t[2 * WD] ^= gtop;
+                }
+                // emit chunk j of c_{k+1} and of s_{k+1} = c_{k+1} + p_{k+1}
+                uint4 *cd = reinterpret_cast<uint4 *>(cnxt + 24 * j);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) cd[q] = make_uint4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
+                if (j == 0) {
+#pragma unroll
+                    for (int i = 0; i <= WD; ++i) t[i] ^= pn[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 24; ++i)
+                    if (24 * j + i < swo) sdst[24 * j + i] = t[i];
+#pragma unroll
+                for (int i = 0; i < 24; ++i) {
+                    t[i] = t[24 + i];
+                    t[24 + i] = 0;
+                }
+            }
+            len += 3 * WD; // deg c_{k+1} = deg c_k + 3D
+            // the words of the next buffer above the new length must read as zero for the last partial chunk
+            {
+                const uint32_t written = 24 * (nchunks + 1);
+                const uint32_t need = ((len + 23) / 24) * 24;
+                for (uint32_t j = written; j < need; ++j) cnxt[j] = 0;
+            }
+            uint32_t *tsw = ccur; ccur = cnxt; cnxt = tsw;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // LOP3 issue-rate probe: the measured denominator of the integer-logic roofline.
 // 8 independent dependency chains per thread, 8 warps per CTA, 8 CTAs per SM.
 // ----------------------------------------------------------------------------------------
