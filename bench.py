@@ -44,7 +44,7 @@ BITMACS_PER_MULREM = 66049 + 49665
 BYTES_PER_MULREM = 96
 # dram__bytes_read.sum + dram__bytes_write.sum of adder_fused_kernel from the ncu --set full capture in profiles/
 # (r01_adder_ncu_details.txt: 42.3 MB + 711.4 MB for 16 384 adds), per add
-NCU_DRAM_BYTES_PER_ADD = (42.303744e6 + 711.399424e6) / 16384
+NCU_DRAM_BYTES_PER_ADD = None  # filled in from the latest ncu capture in profiles/ when available (see profiles/README.md)
 
 
 def measured_peaks():
@@ -449,17 +449,19 @@ def run_ours(args, rank, local_rank, world):
         launch_s = float(np.mean(step_ms)) * 1e-3
         peak_bitmac = lane_ops.value * 32.0
         ach = n * BITMACS_PER_ADD / launch_s
-        roofline = {"kernel": "adder_fused_kernel<8>", "bound": "alu", "achieved": ach / 1e12, "peak": peak_bitmac / 1e12,
+        roofline = {"kernel": "adder_thread_kernel<4> (thread-per-value Karatsuba on IMAD.WIDE + LOP3)", "bound": "alu", "achieved": ach / 1e12, "peak": peak_bitmac / 1e12,
                     "unit": "Tbit-MAC/s", "frac": ach / peak_bitmac, "traffic": None,
-                    "alu_pipe_busy_ncu": 0.918,
+                    "pipes_busy_ncu": {"alu": 0.55, "fmaheavy": 0.55, "issue_slots": 0.43,
+                                       "source": "profiles/r01_adder_thread_ncu_details.txt (75 776 adds)"},
                     "peak_source": f"measured in this run: LOP3 issue-rate probe, {lane_ops.value / 1e12:.2f} T lane-ops/s at ~{mhz.value:.0f} MHz (x32 bits)",
-                    "note": "achieved counts the reference's schoolbook AND-XOR pairs (SURVEY.md A.2); the kernel skips the zero bits "
-                            "of the warp-uniform multiplier and pairs XORs in 3-input LOP3s, so frac can exceed 1"}
+                    "note": "achieved counts the reference's schoolbook AND-XOR pairs (SURVEY.md A.2) against the LOP3-only issue "
+                            "rate; the kernel does the products with Karatsuba on the integer multiplier (FMA pipe) next to "
+                            "LOP3 (ALU pipe), so frac exceeds 1"}
         hbm_peak, src = measured_peaks()
         gbs = n * BYTES_PER_ADD / launch_s / 1e9
-        roofline_hbm = {"kernel": "adder_fused_kernel<8>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": gbs / hbm_peak, "traffic": n * NCU_DRAM_BYTES_PER_ADD,
-                        "traffic_source": "ncu --set full capture at 16 384 adds (profiles/r01_adder_ncu_details.txt), scaled per add; "
+        roofline_hbm = {"kernel": "adder_thread_kernel<4>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": gbs / hbm_peak, "traffic": (n * NCU_DRAM_BYTES_PER_ADD) if NCU_DRAM_BYTES_PER_ADD else None,
+                        "traffic_source": "ncu --set full capture (profiles/r01_adder_thread_ncu_details.txt), scaled per add; "
                                           "algorithmic bytes per launch = %d" % (n * BYTES_PER_ADD),
                         "peak_source": src}
 
@@ -534,7 +536,7 @@ def run_ours(args, rank, local_rank, world):
                     "pairs_per_step": ne, "steps": e2e_steps, "step_ms": e2e_step_ms, "call": "hm_apply2_host (pinned host ciphertexts in/out, 3-stream chunked pipeline)",
                     "matches_device_result": e2e_matches},
             "gpu_launches": int(l_after - l_before),
-            "kernels_in_step": ["adder_fused_kernel<8>"],
+            "kernels_in_step": ["adder_thread_kernel<4>"],
             "clocks": clocks,
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "cpu_baseline": cpu,

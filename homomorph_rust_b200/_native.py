@@ -68,6 +68,7 @@ def lib() -> C.CDLL:
         "hm_context_synchronize": (C.c_int, [vp]),
         "hm_context_kernel_launches": (C.c_uint64, [vp]),
         "hm_context_device": (C.c_int, [vp]),
+        "hm_set_tuning": (C.c_int, [C.c_char_p, C.c_long]),
         "hm_set_secret_key": (C.c_int, [vp, vp, sz]),
         "hm_set_public_key": (C.c_int, [vp, C.POINTER(vp), C.POINTER(sz), sz]),
         "hm_has_secret_key": (C.c_int, [vp]),

@@ -26,6 +26,9 @@ cudaError_t launch_mulrem_fresh_b(const uint64_t *A, const uint64_t *B, uint64_t
                                   int sm_count, cudaStream_t stream); // kernels_b.cu
 }
 
+// tuning knobs (hm_set_tuning): minimum batch size for the thread-per-value adder; < 0 = default (256 values per SM)
+static long g_adder_thread_min = -1;
+
 using hmk::Layout;
 using hmk::MulOp;
 using hmk::View;
@@ -575,6 +578,15 @@ int hm_context_synchronize(hm_context *ctx) {
 }
 uint64_t hm_context_kernel_launches(const hm_context *ctx) { return ctx ? ctx->launches : 0; }
 int hm_context_device(const hm_context *ctx) { return ctx ? ctx->device : -1; }
+
+int hm_set_tuning(const char *key, long value) {
+    if (!key) return HM_ERR_INVALID_ARGUMENT;
+    if (strcmp(key, "adder_thread_min") == 0) {
+        g_adder_thread_min = value;
+        return HM_OK;
+    }
+    return HM_ERR_INVALID_ARGUMENT;
+}
 
 // ---- keys -------------------------------------------------------------------------------------
 static gf2::words words_from_bytes(const uint8_t *bytes, size_t len) { // Polynomial::from_bytes, polynomial.rs:108-122
@@ -1519,7 +1531,9 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                 // HM_ADDER_MODE: 0 / 1 = warp-per-value comb kernel (pair / single uniform branches), m >= 3 = thread-per-value
                 // Karatsuba kernel with m-1 CTAs per SM (default: 4 CTAs of 128 threads, 128 registers)
                 static const int mode = getenv("HM_ADDER_MODE") ? atoi(getenv("HM_ADDER_MODE")) : 5;
-                if (mode >= 3 && wd == 8 && a->L <= 32) { // thread-per-value Karatsuba chain; mode - 1 = CTAs per SM
+                // the thread-per-value kernel needs tens of thousands of values to fill the GPU (one value per thread);
+                // smaller batches (and the chunks of the host pipeline) use the warp-per-value kernel
+                if (mode >= 3 && wd == 8 && n >= (g_adder_thread_min >= 0 ? (size_t)g_adder_thread_min : (size_t)ctx->sm_count * 256)) { // thread-per-value Karatsuba chain; mode - 1 = CTAs per SM
                     const int per_sm = mode - 1;
                     const int blocks = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->sm_count * per_sm);
                     uint32_t *scratch = nullptr;

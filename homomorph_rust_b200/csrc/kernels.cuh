@@ -1342,8 +1342,9 @@ __global__ void __launch_bounds__(128, 5) adder_fused_kernel(const uint64_t *__r
 // Karatsuba on the integer multiplier instead of the warp-uniform comb.  c_k is cut into 24-word chunks; every chunk
 // times the 24 low words of m_k is a 3-way Karatsuba of six 8x8-word products (clmul_kara<8>: 27 single-word leaves
 // each, 16 IMAD.WIDE + 20 LOP3 per leaf), accumulated into a 48-word register window whose upper half is the carry
-// into the next chunk.  The carry polynomials live in a per-thread scratch row in HBM/L2 (two buffers); s_{k+1} is
-// written while c_{k+1} is produced.  No warp cooperation, no shared memory, no idle lanes in the short early steps.
+// into the next chunk.  There is no carry buffer: c_k is read back from the result itself (slot k holds s_k = c_k + p_k,
+// and p_k only touches its first 9 words) while s_{k+1} is written to slot k+1, so the only HBM traffic besides the
+// algorithmic bytes is that one re-read.  No warp cooperation, no shared memory, no idle lanes in the short early steps.
 // ----------------------------------------------------------------------------------------
 template <int O> __device__ __forceinline__ void xor16_at(uint32_t (&t)[48], const uint32_t (&r)[16]) {
 #pragma unroll
@@ -1354,10 +1355,13 @@ template <int O> __device__ __forceinline__ void xor16_at(uint32_t (&t)[48], con
 // memory (per-thread scratch, L1 hits) block by block so that only the 48-word accumulator stays live, and the six
 // products share ONE copy of the 8x8-word Karatsuba code (rolled loop): the kernel is instruction-fetch sensitive.
 __device__ __forceinline__ void mul24_acc(const uint32_t *__restrict__ m, const uint32_t *__restrict__ c, uint32_t (&t)[48]) {
-    auto blk = [](uint32_t (&dst)[8], const uint32_t *src) {
-        const uint4 lo = *reinterpret_cast<const uint4 *>(src), hi = *reinterpret_cast<const uint4 *>(src + 4);
-        dst[0] = lo.x; dst[1] = lo.y; dst[2] = lo.z; dst[3] = lo.w;
-        dst[4] = hi.x; dst[5] = hi.y; dst[6] = hi.z; dst[7] = hi.w;
+    auto blk = [](uint32_t (&dst)[8], const uint32_t *src) { // 8-byte aligned (slot offsets are in u64 words)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint2 w = *reinterpret_cast<const uint2 *>(src + 2 * q);
+            dst[2 * q] = w.x;
+            dst[2 * q + 1] = w.y;
+        }
     };
 #pragma unroll 1
     for (int i = 0; i < 6; ++i) {
@@ -1402,8 +1406,7 @@ static __device__ __noinline__ void kara8_call(const uint32_t *x, const uint32_t
     for (int i = 0; i < 16; ++i) r[i] = o[i];
 }
 
-constexpr int ADT_ROW = 768;                 // words per carry buffer row (>= 737 + one chunk of slack, multiple of 24)
-constexpr int ADT_THREAD_WORDS = 2 * ADT_ROW + 32; // two carry buffers + m_k
+constexpr int ADT_THREAD_WORDS = 64; // per-thread scratch: m_k (24 words) + one staged chunk (24 words)
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) adder_thread_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
@@ -1411,15 +1414,14 @@ __global__ void __launch_bounds__(128, MINB) adder_thread_kernel(const uint64_t 
                                                               uint32_t *__restrict__ scratch) {
     constexpr int WD = 8, WF = 5;
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t *buf0 = scratch + tid * ADT_THREAD_WORDS, *buf1 = buf0 + ADT_ROW, *mbuf = buf1 + ADT_ROW;
+    uint32_t *mbuf = scratch + tid * ADT_THREAD_WORDS, *tmp = mbuf + 32;
     for (uint64_t v = tid; v < n; v += nthreads) {
         const uint64_t *Av = A + v * (uint64_t)L * WF, *Bv = B + v * (uint64_t)L * WF;
         uint32_t *Ov = reinterpret_cast<uint32_t *>(O + v * (uint64_t)lo.value_words);
-        uint32_t *ccur = buf0, *cnxt = buf1;
-        uint32_t len = 0; // words of c_k currently valid in ccur (c_0 = 0)
+        uint32_t len = 0; // words of c_k (c_0 = 0)
         for (uint32_t k = 0; k < L; ++k) {
             // ---- per-bit quantities: p = a + b, g = a * b, m = (1 + g) * p -----------------------------------------
-            uint32_t a[WD], b[WD], p[WD];
+            uint32_t a[WD], b[WD], p[WD + 1];
 #pragma unroll
             for (int j = 0; j < WD / 2; ++j) {
                 const uint64_t x = __ldg(Av + (size_t)k * WF + j), y = __ldg(Bv + (size_t)k * WF + j);
@@ -1430,26 +1432,22 @@ __global__ void __launch_bounds__(128, MINB) adder_thread_kernel(const uint64_t 
 #pragma unroll
             for (int j = 0; j < WD; ++j) p[j] = a[j] ^ b[j];
             const uint32_t ptop = atop ^ btop;
-            // ---- s_k = p_k + c_k (k = 0: c = 0) --------------------------------------------------------------------
-            {
-                uint32_t *dst = Ov + 2 * lo.off[k];
-                const uint32_t wo = 2 * (lo.off[k + 1] - lo.off[k]);
-                if (k == 0) {
+            p[WD] = ptop;
+            if (k == 0) { // s_0 = p_0
+                uint32_t *dst = Ov + 2 * lo.off[0];
+                const uint32_t wo = 2 * (lo.off[1] - lo.off[0]);
 #pragma unroll
-                    for (int j = 0; j < WD; ++j) dst[j] = p[j];
-                    dst[WD] = ptop;
-                    for (uint32_t j = WD + 1; j < wo; ++j) dst[j] = 0;
-                }
-                // for k >= 1 the slot was written while c_k was produced (see below)
+                for (int j = 0; j <= WD; ++j) dst[j] = p[j];
+                for (uint32_t j = WD + 1; j < wo; ++j) dst[j] = 0;
             }
-            if (k + 1 == L) break;
+            if (k + 1 == L) break; // s_k (k >= 1) was written while c_k was produced; no carry out of the last bit
             uint32_t g[2 * WD];
             kara8_call(a, b, g);
             const uint32_t ma = 0u - atop, mb = 0u - btop;
 #pragma unroll
             for (int j = 0; j < WD; ++j) g[WD + j] ^= (b[j] & ma) ^ (a[j] & mb);
             const uint32_t gtop = atop & btop;
-            // next bit's p (to emit s_{k+1} on the fly)
+            // next bit's p (s_{k+1} = c_{k+1} + p_{k+1} is emitted on the fly)
             uint32_t pn[WD + 1];
 #pragma unroll
             for (int j = 0; j < WD / 2; ++j) {
@@ -1461,21 +1459,15 @@ __global__ void __launch_bounds__(128, MINB) adder_thread_kernel(const uint64_t 
             const uint32_t swo = 2 * (lo.off[k + 2] - lo.off[k + 1]);
             if (k == 0) { // c_1 = g_0
 #pragma unroll
-                for (int j = 0; j < 2 * WD; ++j) {
-                    ccur[j] = g[j];
-                    sdst[j] = g[j] ^ (j <= WD ? pn[j] : 0u);
-                }
-                ccur[2 * WD] = gtop;
+                for (int j = 0; j < 2 * WD; ++j) sdst[j] = g[j] ^ (j <= WD ? pn[j] : 0u);
                 sdst[2 * WD] = gtop;
                 for (uint32_t j = 2 * WD + 1; j < swo; ++j) sdst[j] = 0;
-                for (uint32_t j = 2 * WD + 1; j < 24; ++j) ccur[j] = 0;
                 len = 2 * WD + 1;
                 continue;
             }
-            // m = p + g * p : 24 low words + the coefficient of X^768
-            uint32_t m[24];
+            // m = p + g * p : 24 low words (to scratch: read block-wise by mul24_acc) + the coefficient of X^768
             {
-                uint32_t glo[WD], ghi[WD], q0[2 * WD], q1[2 * WD];
+                uint32_t m[24], glo[WD], ghi[WD], q0[2 * WD], q1[2 * WD];
 #pragma unroll
                 for (int j = 0; j < WD; ++j) { glo[j] = g[j]; ghi[j] = g[WD + j]; }
                 kara8_call(glo, p, q0);
@@ -1492,38 +1484,53 @@ __global__ void __launch_bounds__(128, MINB) adder_thread_kernel(const uint64_t 
 #pragma unroll
                 for (int j = 0; j < WD; ++j) m[2 * WD + j] ^= p[j] & mg;
                 m[WD] ^= ptop;
-            }
 #pragma unroll
-            for (int q = 0; q < 6; ++q) reinterpret_cast<uint4 *>(mbuf)[q] = make_uint4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+                for (int q = 0; q < 12; ++q) reinterpret_cast<uint2 *>(mbuf)[q] = make_uint2(m[2 * q], m[2 * q + 1]);
+            }
             const uint32_t mtop = gtop & ptop;
             // ---- c_{k+1} = m c_k + g_k, chunk by chunk; t[0..24) carries the upper half of the previous chunk ---------
+            const uint32_t *cslot = Ov + 2 * lo.off[k]; // s_k = c_k + p_k
             uint32_t t[48];
 #pragma unroll
             for (int i = 0; i < 48; ++i) t[i] = 0;
             const uint32_t nchunks = (len + 23) / 24;
             for (uint32_t j = 0; j <= nchunks; ++j) {
-                if (j < nchunks) mul24_acc(mbuf, ccur + 24 * j, t);
-                if (mtop && j >= 1) { // X^768 * c: chunk j-1 lands in chunk j
-                    const uint32_t *prev = ccur + 24 * (j - 1);
+                if (j < nchunks) {
+                    const uint32_t *cp = cslot + 24 * j;
+                    if (j == 0 || 24 * j + 24 > len) { // chunk touches p_k or the end of the polynomial: stage a clean copy
+                        for (uint32_t i = 0; i < 24; ++i) {
+                            const uint32_t w = 24 * j + i;
+                            uint32_t val = (w < len) ? cslot[w] : 0u;
+                            if (w <= (uint32_t)WD) {
+                                uint32_t pw = p[0];
 #pragma unroll
-                    for (int i = 0; i < 24; ++i) t[i] ^= prev[i];
+                                for (int q = 1; q <= WD; ++q) pw = (w == (uint32_t)q) ? p[q] : pw;
+                                val ^= pw;
+                            }
+                            tmp[i] = val;
+                        }
+                        cp = tmp;
+                    }
+                    mul24_acc(mbuf, cp, t);
+                    if (mtop) { // X^768 * c: chunk j lands in chunk j+1
+#pragma unroll
+                        for (int q = 0; q < 12; ++q) {
+                            const uint2 w = *reinterpret_cast<const uint2 *>(cp + 2 * q);
+                            t[24 + 2 * q] ^= w.x;
+                            t[24 + 2 * q + 1] ^= w.y;
+                        }
+                    }
                 }
                 if (j == 0) {
 #pragma unroll
                     for (int i = 0; i < 2 * WD; ++i) t[i] ^= g[i];
                     t[2 * WD] ^= gtop;
-                }
-                // emit chunk j of c_{k+1} and of s_{k+1} = c_{k+1} + p_{k+1}
-                uint4 *cd = reinterpret_cast<uint4 *>(cnxt + 24 * j);
 #pragma unroll
-                for (int q = 0; q < 6; ++q) cd[q] = make_uint4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]);
-                if (j == 0) {
-#pragma unroll
-                    for (int i = 0; i <= WD; ++i) t[i] ^= pn[i];
+                    for (int i = 0; i <= WD; ++i) t[i] ^= pn[i]; // s_{k+1} = c_{k+1} + p_{k+1}
                 }
 #pragma unroll
-                for (int i = 0; i < 24; ++i)
-                    if (24 * j + i < swo) sdst[24 * j + i] = t[i];
+                for (int q = 0; q < 12; ++q)
+                    if (24 * j + 2 * q < swo) *reinterpret_cast<uint2 *>(sdst + 24 * j + 2 * q) = make_uint2(t[2 * q], t[2 * q + 1]);
 #pragma unroll
                 for (int i = 0; i < 24; ++i) {
                     t[i] = t[24 + i];
@@ -1531,13 +1538,6 @@ __global__ void __launch_bounds__(128, MINB) adder_thread_kernel(const uint64_t 
                 }
             }
             len += 3 * WD; // deg c_{k+1} = deg c_k + 3D
-            // the words of the next buffer above the new length must read as zero for the last partial chunk
-            {
-                const uint32_t written = 24 * (nchunks + 1);
-                const uint32_t need = ((len + 23) / 24) * 24;
-                for (uint32_t j = written; j < need; ++j) cnxt[j] = 0;
-            }
-            uint32_t *tsw = ccur; ccur = cnxt; cnxt = tsw;
         }
     }
 }

@@ -83,6 +83,9 @@ int hm_context_synchronize(hm_context *ctx);
 uint64_t hm_context_kernel_launches(const hm_context *ctx);
 /* CUDA ordinal the context lives on. */
 int hm_context_device(const hm_context *ctx);
+/* Process-wide kernel-selection knobs (tests / experiments).  "adder_thread_min": smallest batch for which the
+ * u32-class adder uses the thread-per-value Karatsuba kernel instead of the warp-per-value kernel (-1 = default). */
+int hm_set_tuning(const char *key, long value);
 
 /* Context::set_secret_key(SecretKey::from_bytes(bytes)) — src/context.rs:153-155, :568-571.
  * `bytes` is SecretKey::to_bytes(): little-endian u64 words (src/polynomial.rs:99-122).

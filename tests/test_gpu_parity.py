@@ -467,3 +467,29 @@ def test_add_fused_other_degrees(oracle, hm, params, dtype, n):
     np.testing.assert_array_equal(ctx.apply2(hm.HomomorphicAddition, ca, cb, generic=True).to_host(), got)
     od, _ = oracle.decrypt(sk, want, L)
     np.testing.assert_array_equal(ctx.decrypt(r).view(np.uint8), od)
+
+
+@pytest.mark.parametrize("dtype,n", [(np.uint32, 300), (np.uint8, 130), (np.uint64, 5)])
+def test_add_thread_kernel_small_batches(oracle, hm, dtype, n):
+    """The thread-per-value Karatsuba adder (default only for >= 256 values per SM) forced on small batches: bit-exact
+    against the oracle and against the warp-per-value kernel, ragged thread counts included."""
+    rng = np.random.default_rng(n)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 23)
+    L = np.dtype(dtype).itemsize * 8
+    a = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    b = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    ma, mb = masks_for(rng, n, L, 128), masks_for(rng, n, L, 128)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    lib = hm.lib()
+    try:
+        assert lib.hm_set_tuning(b"adder_thread_min", 0) == 0
+        r_thread = ctx.apply2(hm.HomomorphicAddition, ca, cb).to_host()
+        assert lib.hm_set_tuning(b"adder_thread_min", 1 << 40) == 0
+        r_warp = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+    finally:
+        lib.hm_set_tuning(b"adder_thread_min", -1)
+    np.testing.assert_array_equal(r_thread, r_warp.to_host())
+    k = min(n, 24)
+    want, _ = oracle.apply(oracle.OP_ADD, oracle_encrypt(oracle, pk, a[:k], ma[: k * L * 16]), oracle_encrypt(oracle, pk, b[:k], mb[: k * L * 16]), L,
+                           threads=oracle.max_threads())
+    np.testing.assert_array_equal(r_thread[:k], expected_padded(want, k, r_warp.slot_words()))
