@@ -44,7 +44,7 @@ BITMACS_PER_MULREM = 66049 + 49665
 BYTES_PER_MULREM = 96
 # dram__bytes_read.sum + dram__bytes_write.sum of adder_fused_kernel from the ncu --set full capture in profiles/
 # (r01_adder_ncu_details.txt: 42.3 MB + 711.4 MB for 16 384 adds), per add
-NCU_DRAM_BYTES_PER_ADD = None  # filled in from the latest ncu capture in profiles/ when available (see profiles/README.md)
+NCU_DRAM_BYTES_PER_ADD = (4.891079e9 + 5.466964e9) / 75776  # ncu capture of adder_thread_kernel<4>, profiles/r01_adder_thread_ncu_details.txt
 
 
 def measured_peaks():

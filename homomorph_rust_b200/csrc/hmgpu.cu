@@ -28,6 +28,7 @@ cudaError_t launch_mulrem_fresh_b(const uint64_t *A, const uint64_t *B, uint64_t
 
 // tuning knobs (hm_set_tuning): minimum batch size for the thread-per-value adder; < 0 = default (256 values per SM)
 static long g_adder_thread_min = -1;
+static long g_mul_thread_min = -1; // minimum (values x chunks) for the thread-per-chunk multiply; < 0 = default (128 per SM)
 
 using hmk::Layout;
 using hmk::MulOp;
@@ -294,8 +295,17 @@ int mul_shape_class(const MulOp &o) {
     return nx * 100 + ny;
 }
 
-int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, size_t cnt, size_t n, size_t smem_general,
+int launch_xor_views(hm_context *ctx, View o, View a, View b, size_t n);
+View null_view();
+
+int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *h_ops, size_t cnt, size_t n, size_t smem_general,
                      uint32_t per_warp_general) {
+    uint32_t xchunks_min = ~0u, xchunks_max = 0;
+    for (size_t i = 0; i < cnt; ++i) {
+        const uint32_t nxw = 2 * std::min(h_ops[i].a.w, h_ops[i].b.w);
+        xchunks_min = std::min(xchunks_min, (nxw + 23) / 24);
+        xchunks_max = std::max(xchunks_max, (nxw + 23) / 24);
+    }
     const dim3 grid_t((unsigned)((n + 127) / 128), (unsigned)cnt);
     switch (cls) {
         case 808: hmk::mul_small_kernel<8, 8><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
@@ -303,6 +313,28 @@ int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, size_t cnt, s
         case 1632: hmk::mul_small_kernel<16, 32><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
         case 3216: hmk::mul_small_kernel<32, 16><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
         default: {
+            // enough (value, chunk) pairs to fill the GPU with one thread each?  -> Karatsuba thread kernel
+            static const int no_thread = getenv("HM_MUL_NO_THREAD") ? atoi(getenv("HM_MUL_NO_THREAD")) : 0;
+            if (!no_thread && (xchunks_min >= 2 || g_mul_thread_min == 0) && (uint64_t)n * xchunks_min >= (g_mul_thread_min >= 0 ? (uint64_t)g_mul_thread_min : (uint64_t)ctx->sm_count * 128) &&
+                (uint64_t)n * cnt * xchunks_max <= ((uint64_t)1 << 22) && cnt <= 65535 && xchunks_max <= 65535) {
+                const size_t threads = (size_t)((n + 127) / 128) * 128 * cnt * xchunks_max;
+                uint32_t *scratch = nullptr;
+                CK(cudaMallocAsync(&scratch, threads * hmk::ADT_THREAD_WORDS * 4, ctx->stream));
+                // outputs are accumulated with atomics: zero them first
+                for (size_t i = 0; i < cnt; ++i) {
+                    const MulOp &o = h_ops[i];
+                    if (o.o.stride == o.o.w) {
+                        CK(cudaMemsetAsync(o.o.base + o.o.off, 0, (size_t)n * o.o.w * 8, ctx->stream));
+                    } else {
+                        int zrc = launch_xor_views(ctx, o.o, null_view(), null_view(), n);
+                        if (zrc != HM_OK) return zrc;
+                    }
+                }
+                const dim3 grid_t3((unsigned)((n + 127) / 128), (unsigned)cnt, (unsigned)xchunks_max);
+                hmk::mul_thread_kernel<<<grid_t3, 128, 0, ctx->stream>>>(d_ops, n, scratch);
+                cudaFreeAsync(scratch, ctx->stream);
+                break;
+            }
             const dim3 grid_w((unsigned)((n + 3) / 4), (unsigned)cnt);
             static const int old_generic = getenv("HM_MUL_OLD") ? atoi(getenv("HM_MUL_OLD")) : 0;
             if (old_generic) {
@@ -355,7 +387,7 @@ int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n) 
             smem = (size_t)per_warp * 4 * 4;
             if (smem > ctx->smem_optin) return HM_ERR_UNSUPPORTED;
         }
-        rc = launch_mul_class(ctx, scls[first], ctx->d_ops + slot + first, last - first, n, smem, per_warp);
+        rc = launch_mul_class(ctx, scls[first], ctx->d_ops + slot + first, sorted.data() + first, last - first, n, smem, per_warp);
         if (rc != HM_OK) return rc;
         first = last;
     }
@@ -583,6 +615,10 @@ int hm_set_tuning(const char *key, long value) {
     if (!key) return HM_ERR_INVALID_ARGUMENT;
     if (strcmp(key, "adder_thread_min") == 0) {
         g_adder_thread_min = value;
+        return HM_OK;
+    }
+    if (strcmp(key, "mul_thread_min") == 0) {
+        g_mul_thread_min = value;
         return HM_OK;
     }
     return HM_ERR_INVALID_ARGUMENT;

@@ -1543,6 +1543,56 @@ __global__ void __launch_bounds__(128, MINB) adder_thread_kernel(const uint64_t 
 }
 
 // ----------------------------------------------------------------------------------------
+// K4c  general products with the Karatsuba-on-the-multiplier machinery of the thread adder: one THREAD per
+// (value, product, 24-word chunk xi of the shorter operand).  The thread multiplies its chunk by the whole longer
+// operand, 24 words at a time (mul24_acc, carry in the upper half of the 48-word window) and XORs the result into the
+// zero-initialised output with 32-bit atomics (threads of different xi overlap by one chunk).  Used for the large
+// products of the multiplier circuit when there are enough (value, chunk) pairs to fill the GPU.
+// ----------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(128, 4) mul_thread_kernel(const MulOp *__restrict__ ops, uint64_t n, uint32_t *__restrict__ scratch) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const MulOp op = ops[blockIdx.y];
+    const uint32_t xi = blockIdx.z;
+    const uint32_t *gx = reinterpret_cast<const uint32_t *>(op.a.base + v * op.a.stride + op.a.off);
+    const uint32_t *gy = reinterpret_cast<const uint32_t *>(op.b.base + v * op.b.stride + op.b.off);
+    uint32_t nx = 2 * op.a.w, ny = 2 * op.b.w;
+    if (nx > ny) { // chunks of the shorter operand are spread over blockIdx.z
+        const uint32_t *tp = gx; gx = gy; gy = tp;
+        const uint32_t tn = nx; nx = ny; ny = tn;
+    }
+    if (24 * xi >= nx) return;
+    const uint64_t slot = ((uint64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    uint32_t *mbuf = scratch + slot * ADT_THREAD_WORDS, *tmp = mbuf + 32;
+    for (uint32_t i = 0; i < 24; ++i) mbuf[i] = (24 * xi + i < nx) ? gx[24 * xi + i] : 0u;
+    uint32_t *go = reinterpret_cast<uint32_t *>(op.o.base + v * op.o.stride + op.o.off);
+    const uint32_t no = 2 * op.o.w;
+    const uint32_t nyc = (ny + 23) / 24;
+    uint32_t t[48];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) t[i] = 0;
+    for (uint32_t j = 0; j <= nyc; ++j) {
+        if (j < nyc) {
+            const uint32_t *cp = gy + 24 * j;
+            if (24 * j + 24 > ny) {
+                for (uint32_t i = 0; i < 24; ++i) tmp[i] = (24 * j + i < ny) ? gy[24 * j + i] : 0u;
+                cp = tmp;
+            }
+            mul24_acc(mbuf, cp, t);
+        }
+        const uint32_t w0 = 24 * (xi + j);
+#pragma unroll
+        for (int i = 0; i < 24; ++i)
+            if (t[i] && w0 + i < no) atomicXor(go + w0 + i, t[i]);
+#pragma unroll
+        for (int i = 0; i < 24; ++i) {
+            t[i] = t[24 + i];
+            t[24 + i] = 0;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // LOP3 issue-rate probe: the measured denominator of the integer-logic roofline.
 // 8 independent dependency chains per thread, 8 warps per CTA, 8 CTAs per SM.
 // ----------------------------------------------------------------------------------------

@@ -403,11 +403,14 @@ def test_encrypt_seeded_device_masks(oracle, hm, params, dtype, n):
         np.testing.assert_array_equal(ctx.decrypt(ct), values)
 
 
-def test_poly_mul_random_shapes(oracle, hm):
+@pytest.mark.parametrize("force_thread", [False, True])
+def test_poly_mul_random_shapes(oracle, hm, force_thread):
     """Randomised widths and degree bounds through every multiply kernel class (thread-per-product Karatsuba for the
-    'k*256 + 1 bit' shapes, warp-cooperative tiles + scalar tail for the rest) against Polynomial::mul of the oracle."""
+    'k*256 + 1 bit' shapes; for the rest warp-cooperative tiles + scalar tail, or — forced here for small batches — the
+    thread-per-chunk Karatsuba kernel with atomic accumulation) against Polynomial::mul of the oracle."""
     rng = np.random.default_rng(2026)
     sk, pk, ctx = setup(oracle, hm, CONFIG_A, 2)
+    hm.lib().hm_set_tuning(b"mul_thread_min", 0 if force_thread else 1 << 50)
     shapes = [(256, 256), (512, 512), (512, 1024), (1024, 512), (1024, 1024), (256, 512), (2048, 1024)]
     for _ in range(25):
         shapes.append((int(rng.integers(0, 3000)), int(rng.integers(0, 3000))))
@@ -430,6 +433,7 @@ def test_poly_mul_random_shapes(oracle, hm):
             rem = ctx.poly_rem(prod)
             wantr = oracle.poly_binop(oracle.POLY_REM, want, sk)
             np.testing.assert_array_equal(rem.to_host(), expected_padded(wantr, n, rem.slot_words()), err_msg=f"rem da={da} db={db}")
+    hm.lib().hm_set_tuning(b"mul_thread_min", -1)
 
 
 def test_empty_batches(oracle, hm):
