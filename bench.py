@@ -146,8 +146,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 GF(2) words", "data": "synthetic (seeded keys, plaintexts and subset masks)",
-        "config": {"workload": "configs[2]: u32 homomorphic add (ripple-carry XOR/AND circuit), d=dp=128, delta=1, tau=128",
-                   "pairs_per_step": n, "note": "bounded sample of the 2^18-pair workload; CPU port of the reference's algorithms"},
+        "config": {"workload": "configs[2]: u32 homomorphic add (ripple-carry XOR/AND circuit) on 2^18 encrypted pairs per GPU, "
+                               "d=dp=128, delta=1, tau=128", "pairs_per_gpu": 1 << 18, "bits": L,
+                   "pairs_per_step": n, "note": "each step is a bounded sample of the 2^18-pair workload on the host cores; CPU port "
+                                                "of the reference's algorithms (the Rust reference cannot be built in this image)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n} pairs per step x {args.steps} steps, {threads} threads over independent values"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
