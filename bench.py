@@ -326,6 +326,9 @@ def run_ours(args, rank, local_rank, world):
                            "hbm_GBps": pairs * BYTES_PER_MULREM / s / 1e9, "hbm_frac": pairs * BYTES_PER_MULREM / s / 1e9 / hbm_peak,
                            "Tbitmac_per_s": pairs * BITMACS_PER_MULREM / s / 1e12,
                            "alu_frac": pairs * BITMACS_PER_MULREM / s / (lane_ops.value * 32.0)}
+        k8m = C.c_double(0.0)
+        lib.hm_measure_kara8_peak(ctx._h, C.byref(k8m))
+        extra["mulrem"]["product_pipe_frac"] = pairs / s / k8m.value  # one 8x8-word product per pair (+ the table fold)
         mr.free()
         # decrypt after add (HBM bound: 46 912 B per value)
         dout = torch.empty(n * 4, dtype=torch.uint8, device=f"cuda:{local_rank}")
@@ -470,6 +473,13 @@ def run_ours(args, rank, local_rank, world):
                     "note": "achieved counts the reference's schoolbook AND-XOR pairs (SURVEY.md A.2) against the LOP3-only issue "
                             "rate; the kernel does the products with Karatsuba on the integer multiplier (FMA pipe) next to "
                             "LOP3 (ALU pipe), so frac exceeds 1"}
+        k8 = C.c_double(0.0)
+        lib.hm_measure_kara8_peak(ctx._h, C.byref(k8))
+        KARA8_PER_ADD = 1 + 30 * 3 + 6 * 465  # per bit: g (k=0), g, g_lo*p, g_hi*p (k=1..30); chain: sum_k ceil((24k-7)/24) = 465 chunks x 6
+        roofline["product_pipe"] = {"bound": "fma-heavy pipe (432 IMAD.WIDE per 8x8-word Karatsuba product)",
+                                    "achieved": n * KARA8_PER_ADD / launch_s / 1e9, "peak": k8.value / 1e9, "unit": "G 8x8-word products/s",
+                                    "frac": n * KARA8_PER_ADD / launch_s / k8.value,
+                                    "peak_source": "measured in this run: hm_measure_kara8_peak (the product in isolation, 16 warps/SM)"}
         hbm_peak, src = measured_peaks()
         gbs = n * BYTES_PER_ADD / launch_s / 1e9
         roofline_hbm = {"kernel": "adder_thread_kernel<4>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
         "hm_apply2_generic": (C.c_int, [vp, C.c_int, vp, vp, C.POINTER(vp)]),
         "hm_apply2_into": (C.c_int, [vp, C.c_int, vp, vp, vp]),
         "hm_measure_alu_peak": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "hm_measure_kara8_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
         "hm_op_min_d_over_delta": (C.c_int, [C.c_int]),
         "hm_result_slot_words": (C.c_int, [vp, C.c_int, C.c_uint32, u32p, u32p, u32p]),
         "hm_apply2_host": (C.c_int, [vp, C.c_int, sz, C.c_uint32, u32p, vp, u32p, vp, vp]),

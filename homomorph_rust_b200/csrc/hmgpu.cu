@@ -1909,6 +1909,34 @@ int hm_measure_alu_peak(hm_context *ctx, double *lop3_lane_ops_per_s, double *sm
     return HM_OK;
 }
 
+int hm_measure_kara8_peak(hm_context *ctx, double *products_per_s) {
+    if (!ctx || !products_per_s) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    const int blocks = ctx->sm_count * 4, threads = 128, iters = 1500;
+    uint32_t *sink = nullptr;
+    CK(cudaMalloc(&sink, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    hmk::kara8_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(sink, iters, 0x9e3779b9u);
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, ctx->stream);
+        hmk::kara8_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(sink, iters, 0x9e3779b9u + rep);
+        cudaEventRecord(e1, ctx->stream);
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = std::max(best, (double)blocks * threads * iters / (ms * 1e-3));
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *products_per_s = best;
+    return HM_OK;
+}
+
 // ---- host-side helpers ---------------------------------------------------------------------------
 uint32_t hm_fresh_slot_words(const hm_context *ctx) {
     if (!ctx) return 0;

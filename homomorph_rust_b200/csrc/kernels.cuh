@@ -1619,4 +1619,28 @@ static __global__ void __launch_bounds__(256) lop3_peak_kernel(uint32_t *sink, u
     if (threadIdx.x == 0) clk[blockIdx.x] = (unsigned long long)(t1 - t0);
 }
 
+// 8x8-word Karatsuba product rate probe: the denominator of the roofline of the thread-per-value adder and of the fused
+// mul+rem, both of which are chains of these products (bound by the FMA-heavy pipe: 432 IMAD.WIDE per product).
+static __global__ void __launch_bounds__(128, 4) kara8_peak_kernel(uint32_t *sink, int iters, uint32_t seed) {
+    uint32_t a[8], b[8], r[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = seed * (threadIdx.x + 1) + i;
+        b[i] = seed ^ (blockIdx.x * 977u + i);
+    }
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        clmul_kara<8>(a, b, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a[i] ^= r[i];
+            b[i] += r[8 + i];
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc ^= a[i] ^ b[i];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 } // namespace hmk

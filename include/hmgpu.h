@@ -211,6 +211,10 @@ int hm_poly_mulrem_into(hm_context *ctx, const hm_batch *a, const hm_batch *b, h
  * second (x32 = bit-MACs/s: one `r ^= a & m` is 32 AND-XOR pairs) and the SM clock seen meanwhile.
  * This is the measured denominator of the integer-logic roofline of the multiply kernels. */
 int hm_measure_alu_peak(hm_context *ctx, double *lop3_lane_ops_per_s, double *sm_clock_mhz);
+/* Rate of the 8x8-word (256 x 256 bit) Karatsuba carry-less product in isolation, products per second on the whole
+ * device: the measured ceiling of the kernels that are chains of such products (thread-per-value adder: 2 881 per
+ * u32 add; fused mul+rem at d=d'=128: 1 per pair, plus the fold). */
+int hm_measure_kara8_peak(hm_context *ctx, double *products_per_s);
 
 /* ---- Host-side helpers (no GPU needed) ---------------------------------------------------- */
 /* Worst-case slot widths of a freshly encrypted value: (d+dp)/64+1 words per slot. */
