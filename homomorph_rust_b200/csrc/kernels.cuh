@@ -8,13 +8,19 @@
 // (little endian), since the SM integer datapath is 32 bits wide.
 //
 // Kernel -> reference map
-//   encrypt_*            CipheredBit::cipher        src/cipher.rs:99-115 (+ loop :180-185)
-//   decrypt_*            CipheredBit::decipher      src/cipher.rs:119-122 (+ packing :227-237)
-//   xor_* / not_kernel   Polynomial::add, gate_xor/not   src/polynomial.rs:190-243, common.rs:21-35
-//   mul_views_kernel     Polynomial::mul            src/polynomial.rs:252-310
-//   rem_*                Polynomial::rem            src/polynomial.rs:316-365
-//   mulrem_fresh_kernel  mul followed by rem (the BASELINE "mul+rem" unit)
-//   adder_fused_kernel   add_internal               src/impls/numbers/common.rs:37-56
+//   encrypt_tab6 / encrypt_tab / encrypt_generic   CipheredBit::cipher     src/cipher.rs:99-115 (+ loop :180-185)
+//   mask_fill_kernel (Philox4x32-10)               CipheredBit::part       src/cipher.rs:92-97 (seeded replacement)
+//   decrypt_uniform / decrypt_value_tma / decrypt_slots   CipheredBit::decipher   src/cipher.rs:119-122 (+ packing :227-237)
+//   xor_* / not_kernel                             Polynomial::add, gate_xor/not   src/polynomial.rs:190-243, common.rs:21-35
+//   mul_small / mul_thread / mul_warp / mul_views  Polynomial::mul         src/polynomial.rs:252-310
+//   rem_fold / rem_generic                         Polynomial::rem         src/polynomial.rs:316-365
+//   mulrem_fresh_kernel                            mul followed by rem (the BASELINE "mul+rem" unit)
+//   adder_thread_kernel / adder_fused_kernel       add_internal            src/impls/numbers/common.rs:37-56
+//   (mul_unsigned_internal, common.rs:66-105, is a host-planned sequence of the multiply / xor kernels: hmgpu.cu)
+//
+// Building blocks: clmul32_imad (32x32 carry-less product on the integer multiplier), clmul_kara<N> (Karatsuba over
+// words), mul24_acc (24x24-word product as six 8x8-word Karatsubas), clmul_regs (shift/mask schoolbook, ALU only),
+// fold_word (CRC-style remainder step), TMA 1-D bulk copy + mbarrier helpers.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
