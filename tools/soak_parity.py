@@ -1,0 +1,86 @@
+"""Parity soak: the CUDA engine against the CPU oracle on larger seeded samples than the unit tests use, every output
+word compared.  Prints one line per check; exit code 1 on any mismatch.  (python tools/soak_parity.py on a B200)"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import homomorph_rust_b200 as hm  # noqa: E402
+from helpers import engine_context, expected_padded, keys, oracle_encrypt  # noqa: E402
+from oracle import hmoracle as orc  # noqa: E402
+
+A = (128, 128, 1, 128)
+ok = True
+
+
+def check(name, got, want, t0):
+    global ok
+    same = bool(np.array_equal(got, want))
+    ok &= same
+    print(f"{'OK  ' if same else 'FAIL'} {name:58s} {got.size:>12d} words compared  {time.time() - t0:6.1f} s", flush=True)
+
+
+def rb(seed, n):
+    return np.frombuffer(np.random.default_rng(seed).bytes(n), dtype=np.uint8)
+
+
+sk, pk, skb, pkb = keys(orc, *A, 777)
+ctx = engine_context(hm, *A, skb, pkb)
+lib = hm.lib()
+rng = np.random.default_rng(42)
+T = orc.max_threads()
+
+# encrypt / decrypt
+t0 = time.time(); n = 100_000
+v = rng.integers(0, 2**32, size=n, dtype=np.uint32); m = rb(1, n * 512)
+ct = ctx.encrypt(v, m); want = oracle_encrypt(orc, pk, v, m)
+check("encrypt u32 (table kernel)", ct.to_host(), expected_padded(want, n, [5] * 32), t0)
+check("decrypt fresh u32", ctx.decrypt(ct).view(np.uint8), orc.decrypt(sk, want, 32, threads=T)[0], t0)
+
+# u32 add: thread-per-value kernel and warp-per-value kernel
+for name, tune, n in (("u32 add, thread-per-value Karatsuba kernel", 0, 20_000), ("u32 add, warp-per-value comb kernel", 1 << 40, 6_000)):
+    t0 = time.time()
+    a = rng.integers(0, 2**32, size=n, dtype=np.uint32); b = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    ma, mb = rb(2 + n, n * 512), rb(3 + n, n * 512)
+    lib.hm_set_tuning(b"adder_thread_min", tune)
+    s = ctx.apply2(hm.HomomorphicAddition, ctx.encrypt(a, ma), ctx.encrypt(b, mb))
+    lib.hm_set_tuning(b"adder_thread_min", -1)
+    ws, _ = orc.apply(orc.OP_ADD, oracle_encrypt(orc, pk, a, ma), oracle_encrypt(orc, pk, b, mb), 32, threads=T)
+    check(name, s.to_host(), expected_padded(ws, n, s.slot_words()), t0)
+    check("  decrypt after add", ctx.decrypt(s).view(np.uint8), orc.decrypt(sk, ws, 32, threads=T)[0], t0)
+    del s
+
+# fused mul+rem
+t0 = time.time(); n = 40_000
+a = rng.integers(0, 2**32, size=n, dtype=np.uint32); b = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+ma, mb = rb(5, n * 512), rb(6, n * 512)
+r = ctx.poly_mulrem(ctx.encrypt(a, ma), ctx.encrypt(b, mb))
+wr, _ = orc.poly_mulrem(oracle_encrypt(orc, pk, a, ma), oracle_encrypt(orc, pk, b, mb), sk, threads=T)
+check("mul+rem on fresh pairs (1.28 M pairs)", r.to_host(), expected_padded(wr, n, [2] * 32), t0)
+
+# u8 multiplier circuit (thread-per-chunk products)
+t0 = time.time(); n = 20_000
+a = rng.integers(0, 256, size=n, dtype=np.uint8); b = rng.integers(0, 256, size=n, dtype=np.uint8)
+ma, mb = rb(7, n * 128), rb(8, n * 128)
+p = ctx.apply2(hm.HomomorphicMultiplication, ctx.encrypt(a, ma), ctx.encrypt(b, mb))
+wp, _ = orc.apply(orc.OP_MUL, oracle_encrypt(orc, pk, a, ma), oracle_encrypt(orc, pk, b, mb), 8, threads=T)
+check("u8 multiply circuit", p.to_host(), expected_padded(wp, n, p.slot_words()), t0)
+check("  decrypt after mul", ctx.decrypt(p), orc.decrypt(sk, wp, 8, threads=T)[0], t0)
+
+# AND / OR gates
+t0 = time.time(); n = 30_000
+a = rng.integers(0, 2**32, size=n, dtype=np.uint32); b = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+ma, mb = rb(9, n * 512), rb(10, n * 512)
+ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+oa, ob = oracle_encrypt(orc, pk, a, ma), oracle_encrypt(orc, pk, b, mb)
+for op, oop, nm in ((hm.HomomorphicAndGate, orc.OP_AND, "AND"), (hm.HomomorphicOrGate, orc.OP_OR, "OR")):
+    g = ctx.apply2(op, ca, cb)
+    wg, _ = orc.apply(oop, oa, ob, 32, threads=T)
+    check(f"{nm} gate on fresh u32 batches", g.to_host(), expected_padded(wg, n, g.slot_words()), t0)
+
+print("ALL OK" if ok else "MISMATCH")
+sys.exit(0 if ok else 1)
