@@ -413,7 +413,7 @@ def run_ours(args, rank, local_rank, world):
         extra["u8_mul"] = {"value": n8 / (t2 - t1), "unit": "u8 muls/s", "pairs": n8, "ms": (t2 - t1) * 1e3, "first_call_ms": (t1 - t0) * 1e3,
                            "ms_each": [round(x * 1e3, 3) for x in t8],
                            "kernel_launches": int(l1 - l0), "correct_frac": float(np.mean(d8 == a8 * b8)),
-                           "note": "host-planned sequence of mul_small / mul_thread / mul_warp / xor kernels over a per-value arena in HBM; wall clock incl. launches, median of 3"}
+                           "note": "column-batched circuit: per column one prefix-XOR launch + one batch of independent carry products (mul_small on a side stream, mul_thread32 for the big ones) over a per-value arena in HBM; wall clock incl. launches, median of 3"}
         for o8 in (p8, p8b, c8a, c8b):
             o8.free()
         # config 5 (stress): d=d'=512, tau=256, delta=8 fused mul+rem on 2^20 fresh pairs

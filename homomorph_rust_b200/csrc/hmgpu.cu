@@ -29,6 +29,8 @@ cudaError_t launch_mulrem_fresh_b(const uint64_t *A, const uint64_t *B, uint64_t
 // tuning knobs (hm_set_tuning): minimum batch size for the thread-per-value adder; < 0 = default (256 values per SM)
 static long g_adder_thread_min = -1;
 static long g_mul_thread_min = -1; // minimum (values x chunks) for the thread-per-chunk multiply; < 0 = default (128 per SM)
+static long g_mul_thread_chunk = 32; // 24 = the first thread-per-chunk kernel (3-way Karatsuba chunks)
+static long g_mul_circuit_seq = 0;  // 1 = launch the multiplier circuit's carry products one by one (the first plan)
 
 using hmk::Layout;
 using hmk::MulOp;
@@ -52,6 +54,8 @@ struct hm_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side_stream = nullptr; // runs the small products of a multiplier column beside the big ones
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t launches = 0;
     std::string last_error;
     int sm_count = 148;
@@ -256,6 +260,7 @@ int ensure_ops(hm_context *ctx, size_t n_ops, size_t *first_slot) {
     constexpr size_t RING = 16384;
     if (!ctx->d_ops || ctx->d_ops_cap < n_ops) {
         CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->side_stream));
         if (ctx->d_ops) cudaFree(ctx->d_ops);
         if (ctx->h_ops) cudaFreeHost(ctx->h_ops);
         ctx->d_ops = nullptr;
@@ -268,6 +273,7 @@ int ensure_ops(hm_context *ctx, size_t n_ops, size_t *first_slot) {
     }
     if (ctx->ops_cursor + n_ops > ctx->d_ops_cap) {
         CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->side_stream));
         ctx->ops_cursor = 0;
     }
     *first_slot = ctx->ops_cursor;
@@ -299,12 +305,15 @@ int launch_xor_views(hm_context *ctx, View o, View a, View b, size_t n);
 View null_view();
 
 int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *h_ops, size_t cnt, size_t n, size_t smem_general,
-                     uint32_t per_warp_general) {
-    uint32_t xchunks_min = ~0u, xchunks_max = 0;
+                     uint32_t per_warp_general, bool outputs_zeroed) {
+    // thread-per-chunk kernels: chunks of the shorter operand (32-word chunks see "low words + top coefficient" operands)
+    const bool chunk32 = g_mul_thread_chunk != 24;
+    uint32_t xchunks_max = 0;
+    uint64_t xchunks_sum = 0;
     for (size_t i = 0; i < cnt; ++i) {
-        const uint32_t nxw = 2 * std::min(h_ops[i].a.w, h_ops[i].b.w);
-        xchunks_min = std::min(xchunks_min, (nxw + 23) / 24);
-        xchunks_max = std::max(xchunks_max, (nxw + 23) / 24);
+        const uint32_t xc = chunk32 ? (hmk::thread_mul_shape(h_ops[i]).nx + 31) / 32 : (2 * std::min(h_ops[i].a.w, h_ops[i].b.w) + 23) / 24;
+        xchunks_max = std::max(xchunks_max, xc);
+        xchunks_sum += xc;
     }
     const dim3 grid_t((unsigned)((n + 127) / 128), (unsigned)cnt);
     switch (cls) {
@@ -315,13 +324,13 @@ int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *
         default: {
             // enough (value, chunk) pairs to fill the GPU with one thread each?  -> Karatsuba thread kernel
             static const int no_thread = getenv("HM_MUL_NO_THREAD") ? atoi(getenv("HM_MUL_NO_THREAD")) : 0;
-            if (!no_thread && (xchunks_min >= 2 || g_mul_thread_min == 0) && (uint64_t)n * xchunks_min >= (g_mul_thread_min >= 0 ? (uint64_t)g_mul_thread_min : (uint64_t)ctx->sm_count * 128) &&
+            if (!no_thread && (uint64_t)n * xchunks_sum >= (g_mul_thread_min >= 0 ? (uint64_t)g_mul_thread_min : (uint64_t)ctx->sm_count * 128) &&
                 (uint64_t)n * cnt * xchunks_max <= ((uint64_t)1 << 22) && cnt <= 65535 && xchunks_max <= 65535) {
                 const size_t threads = (size_t)((n + 127) / 128) * 128 * cnt * xchunks_max;
                 uint32_t *scratch = nullptr;
                 CK(cudaMallocAsync(&scratch, threads * hmk::ADT_THREAD_WORDS * 4, ctx->stream));
-                // outputs are accumulated with atomics: zero them first
-                for (size_t i = 0; i < cnt; ++i) {
+                // outputs are accumulated with atomics: zero them first (unless the caller already did)
+                for (size_t i = 0; i < cnt && !outputs_zeroed; ++i) {
                     const MulOp &o = h_ops[i];
                     if (o.o.stride == o.o.w) {
                         CK(cudaMemsetAsync(o.o.base + o.o.off, 0, (size_t)n * o.o.w * 8, ctx->stream));
@@ -331,7 +340,8 @@ int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *
                     }
                 }
                 const dim3 grid_t3((unsigned)((n + 127) / 128), (unsigned)cnt, (unsigned)xchunks_max);
-                hmk::mul_thread_kernel<<<grid_t3, 128, 0, ctx->stream>>>(d_ops, n, scratch);
+                if (chunk32) hmk::mul_thread32_kernel<<<grid_t3, 128, 0, ctx->stream>>>(d_ops, n, scratch);
+                else hmk::mul_thread_kernel<<<grid_t3, 128, 0, ctx->stream>>>(d_ops, n, scratch);
                 cudaFreeAsync(scratch, ctx->stream);
                 break;
             }
@@ -349,7 +359,7 @@ int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *
     return post_launch(ctx, "mul kernel");
 }
 
-int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n) {
+int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n, bool outputs_zeroed = false) {
     if (ops_in.empty() || n == 0) return HM_OK;
     // group by shape class (stable), one launch per class
     std::vector<MulOp> ops(ops_in);
@@ -387,7 +397,8 @@ int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n) 
             smem = (size_t)per_warp * 4 * 4;
             if (smem > ctx->smem_optin) return HM_ERR_UNSUPPORTED;
         }
-        rc = launch_mul_class(ctx, scls[first], ctx->d_ops + slot + first, sorted.data() + first, last - first, n, smem, per_warp);
+        rc = launch_mul_class(ctx, scls[first], ctx->d_ops + slot + first, sorted.data() + first, last - first, n, smem, per_warp,
+                              outputs_zeroed);
         if (rc != HM_OK) return rc;
         first = last;
     }
@@ -550,6 +561,12 @@ int hm_context_create(uint16_t d, uint16_t dp, uint16_t delta, uint16_t tau, int
         return HM_ERR_CUDA;
     }
     ctx->own_stream = true;
+    if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return HM_ERR_CUDA;
+    }
     {   // keep freed blocks in the stream-ordered pool instead of returning them to the driver at every sync
         cudaMemPool_t pool = nullptr;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
@@ -574,6 +591,12 @@ void hm_context_destroy(hm_context *ctx) {
     clear_public(ctx);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
     if (ctx->h_ops) cudaFreeHost(ctx->h_ops);
+    if (ctx->side_stream) {
+        cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamDestroy(ctx->side_stream);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -619,6 +642,15 @@ int hm_set_tuning(const char *key, long value) {
     }
     if (strcmp(key, "mul_thread_min") == 0) {
         g_mul_thread_min = value;
+        return HM_OK;
+    }
+    if (strcmp(key, "mul_thread_chunk") == 0) {
+        if (value != 24 && value != 32) return HM_ERR_INVALID_ARGUMENT;
+        g_mul_thread_chunk = value;
+        return HM_OK;
+    }
+    if (strcmp(key, "mul_circuit_sequential") == 0) {
+        g_mul_circuit_seq = value;
         return HM_OK;
     }
     return HM_ERR_INVALID_ARGUMENT;
@@ -1367,7 +1399,7 @@ static int add_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
 }
 
 // generic unsigned multiplier circuit, reference common.rs:66-105
-static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
+static int mul_generic_seq(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
     const uint32_t L = a->L;
     const size_t n = a->n;
     struct Obj {
@@ -1496,6 +1528,130 @@ static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
             View rr = r;
             rr.w = std::min(r.w, x.w);
             rc = launch_xor_views(ctx, rr, rr, x, n);
+        }
+    }
+    cudaFreeAsync(arena, ctx->stream);
+    return rc;
+}
+
+// Column-batched plan of the same circuit.  In column i the reference XORs the items x_1..x_m (the column's partial
+// products, then the carries of column i-1, common.rs:78-101) into result[i] one at a time and, before each XOR, pushes
+// the carry x_t * result[i]; result[i] at that moment is the prefix P_{t-1} = x_1 ^ ... ^ x_{t-1}.  So the same carries
+// (the same polynomials, bit for bit) are c_t = x_t * P_{t-1}: one prefix pass writes P_2..P_{m-1} and result[i] = P_m,
+// and the column's m-1 products are independent and go out as one batch of launches.  ~30 launches per u8 multiply
+// instead of ~180, and each product launch has enough (value, chunk) threads to fill the GPU.
+static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
+    if (g_mul_circuit_seq) return mul_generic_seq(ctx, a, b, o);
+    const uint32_t L = a->L;
+    const size_t n = a->n;
+    struct Obj {
+        uint64_t off; // u64 words from the start of a value's arena
+        uint64_t degb;
+    };
+    uint64_t cursor = 0;
+    auto alloc = [&](uint64_t degb) {
+        Obj ob{cursor, degb};
+        cursor += degb / 64 + 1;
+        return ob;
+    };
+    std::vector<std::vector<Obj>> pp(L, std::vector<Obj>(L));
+    for (uint32_t j = 0; j < L; ++j)
+        for (uint32_t k = 0; j + k < L; ++k) pp[j][k] = alloc(a->degb[j] + b->degb[k]);
+    const uint64_t pp_words = cursor;
+    struct Column {
+        std::vector<Obj> items, prefix, carry; // prefix[t] = P_{t+1} for 1 <= t+1 < m-1 (arena); carry[t] = x_{t+1} * P_t
+    };
+    std::vector<Column> cols(L);
+    std::vector<Obj> incoming; // non-zero carries of the previous column, in push order
+    for (uint32_t i = 0; i < L; ++i) {
+        Column &c = cols[i];
+        for (uint32_t j = 0; j <= i; ++j) c.items.push_back(pp[j][i - j]);
+        c.items.insert(c.items.end(), incoming.begin(), incoming.end());
+        incoming.clear();
+        uint64_t dres = c.items[0].degb;
+        for (size_t t = 1; t < c.items.size(); ++t) {
+            if (i + 1 < L) {
+                // P_t covers x_1..x_t; P_1 is x_1 itself, later ones need storage (the last prefix is the result slot)
+                if (t >= 2) c.prefix.push_back(alloc(dres));
+                c.carry.push_back(alloc(c.items[t].degb + dres));
+                incoming.push_back(c.carry.back());
+            }
+            dres = std::max(dres, c.items[t].degb);
+        }
+        // L = 8 has at most 36 items per column; the bounds cannot differ (both follow result_bounds)
+        if (c.items.size() > hmk::PREFIX_MAX_ITEMS || dres != o->degb[i]) return mul_generic_seq(ctx, a, b, o);
+    }
+    const size_t arena_words = cursor;
+    if (arena_words >> 32) return HM_ERR_UNSUPPORTED;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    if ((double)n * arena_words * 8.0 > 0.9 * (double)free_b) return HM_ERR_UNSUPPORTED;
+    uint64_t *arena = nullptr;
+    CK(cudaMallocAsync(&arena, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
+    // carries are accumulated with atomics by the thread-per-chunk kernel: clear the arena once instead of per product
+    CK(cudaMemsetAsync(arena, 0, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
+    (void)pp_words;
+    auto aview = [&](const Obj &ob) {
+        View v;
+        v.base = arena;
+        v.stride = arena_words;
+        v.off = (uint32_t)ob.off;
+        v.w = (uint32_t)(ob.degb / 64 + 1);
+        v.deg = ob.degb;
+        return v;
+    };
+    int rc = HM_OK;
+    { // all partial products in one batch (independent)
+        std::vector<MulOp> ops;
+        for (uint32_t j = 0; j < L; ++j)
+            for (uint32_t k = 0; j + k < L; ++k) ops.push_back(MulOp{slot_view(a, j), slot_view(b, k), aview(pp[j][k])});
+        rc = launch_mul_ops(ctx, ops, n, true);
+    }
+    std::vector<MulOp> pre, ops, small;
+    for (uint32_t i = 0; i < L && rc == HM_OK; ++i) {
+        const Column &c = cols[i];
+        const size_t m = c.items.size();
+        pre.clear();
+        ops.clear();
+        for (size_t t = 0; t < m; ++t) {
+            View dst = null_view();
+            if (t + 1 == m) dst = slot_view(o, i);
+            else if (t >= 1 && !c.prefix.empty()) dst = aview(c.prefix[t - 1]);
+            pre.push_back(MulOp{aview(c.items[t]), null_view(), dst});
+        }
+        size_t slot = 0;
+        rc = ensure_ops(ctx, pre.size(), &slot);
+        if (rc != HM_OK) break;
+        memcpy(ctx->h_ops + slot, pre.data(), pre.size() * sizeof(MulOp));
+        CK(cudaMemcpyAsync(ctx->d_ops + slot, ctx->h_ops + slot, pre.size() * sizeof(MulOp), cudaMemcpyHostToDevice, ctx->stream));
+        const uint32_t width = o->w[i];
+        hmk::prefix_xor_kernel<<<grid_for(ctx, (uint64_t)n * width, 256, 16), 256, 0, ctx->stream>>>(ctx->d_ops + slot, (uint32_t)pre.size(),
+                                                                                                   width, n);
+        LAUNCHED("prefix_xor_kernel");
+        if (i + 1 < L) {
+            // the column's products are independent: the big ones (thread-per-chunk kernel) go on the context's stream,
+            // the small register-resident ones on the side stream so that they fill the big launch's tail
+            small.clear();
+            for (size_t t = 1; t < m; ++t) {
+                const MulOp op{aview(c.items[t]), t == 1 ? aview(c.items[0]) : aview(c.prefix[t - 2]), aview(c.carry[t - 1])};
+                (mul_shape_class(op) ? small : ops).push_back(op);
+            }
+            const bool fork = !small.empty() && !ops.empty();
+            if (fork) {
+                CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+                CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+            }
+            rc = launch_mul_ops(ctx, ops, n, true);
+            if (rc == HM_OK && !small.empty()) {
+                cudaStream_t main_stream = ctx->stream;
+                if (fork) ctx->stream = ctx->side_stream;
+                rc = launch_mul_ops(ctx, small, n, true);
+                ctx->stream = main_stream;
+                if (fork) {
+                    CK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+                    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+                }
+            }
         }
     }
     cudaFreeAsync(arena, ctx->stream);

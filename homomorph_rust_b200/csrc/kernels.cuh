@@ -543,6 +543,41 @@ static __global__ void __launch_bounds__(256) xor_views_kernel(View o, View a, V
     }
 }
 
+// Running XOR over a list of slots: ops[t].a is the t-th item x_t, ops[t].o (when its base is not null) receives the
+// prefix x_0 ^ ... ^ x_t.  One thread per (value, word); `width` is the widest destination.  Used by the multiplier
+// circuit (reference src/impls/numbers/common.rs:78-101): the carries of one column are x_t * (x_0 ^ ... ^ x_{t-1}),
+// so with the prefixes materialised all of a column's products are independent and go out in one launch.
+constexpr uint32_t PREFIX_MAX_ITEMS = 64;
+static __global__ void __launch_bounds__(256) prefix_xor_kernel(const MulOp *__restrict__ ops, uint32_t cnt, uint32_t width, uint64_t n) {
+    // descriptors once per CTA into shared memory (cnt <= PREFIX_MAX_ITEMS, checked by the host)
+    __shared__ View s_a[PREFIX_MAX_ITEMS], s_o[PREFIX_MAX_ITEMS];
+    for (uint32_t t = threadIdx.x; t < cnt; t += blockDim.x) {
+        s_a[t] = ops[t].a;
+        s_o[t] = ops[t].o;
+    }
+    __syncthreads();
+    const uint64_t total = n * width;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = i / width;
+        const uint32_t j = (uint32_t)(i % width);
+        uint64_t acc = 0;
+        for (uint32_t t0 = 0; t0 < cnt; t0 += 4) { // four items in flight: the loads of a group do not depend on each other
+            uint64_t x[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t t = t0 + u;
+                x[u] = (t < cnt && j < s_a[t].w) ? __ldg(s_a[t].base + v * s_a[t].stride + s_a[t].off + j) : 0;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t t = t0 + u;
+                acc ^= x[u];
+                if (t < cnt && s_o[t].base && j < s_o[t].w) s_o[t].base[v * s_o[t].stride + s_o[t].off + j] = acc;
+            }
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 // K4  generic carry-less multiply, one warp per product     reference src/polynomial.rs:252-310
 //
@@ -1596,6 +1631,130 @@ static __global__ void __launch_bounds__(128, 4) mul_thread_kernel(const MulOp *
             t[24 + i] = 0;
         }
     }
+}
+
+// t ^= m * c for 32-word m and c: two Karatsuba levels over 8-word blocks = nine 8x8-word products (mul24_acc's
+// 3-way split needs six for 24 words: 96 word pairs per product there, 114 here).  Rolled like mul24_acc: one copy
+// of the 8x8-word code; leaf i = 3 * top + sub with top/sub in {low, high, middle}.
+template <int O> __device__ __forceinline__ void xor16_at64(uint32_t (&t)[64], const uint32_t (&r)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[O + i] ^= r[i];
+}
+__device__ __forceinline__ void mul32_acc(const uint32_t *__restrict__ m, const uint32_t *__restrict__ c, uint32_t (&t)[64]) {
+#pragma unroll 1
+    for (int i = 0; i < 9; ++i) {
+        // blocks XORed into the leaf operand: bit b = 8-word block b.  top: ll {0,1}, hh {2,3}, mid {0^2, 1^3}
+        const uint32_t sel = (uint32_t)(0xFA5C84321ull >> (4 * i)) & 0xFu; // leaves 0..8: 1, 2, 3, 4, 8, C, 5, A, F
+        uint32_t x[8], y[8], r[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = y[q] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (sel >> b & 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint2 u = *reinterpret_cast<const uint2 *>(m + 8 * b + 2 * q);
+                    const uint2 w = *reinterpret_cast<const uint2 *>(c + 8 * b + 2 * q);
+                    x[2 * q] ^= u.x; x[2 * q + 1] ^= u.y;
+                    y[2 * q] ^= w.x; y[2 * q + 1] ^= w.y;
+                }
+            }
+        }
+        clmul_kara<8>(x, y, r);
+        switch (i) { // destination offsets = {top bases} + {sub offsets}: ll {0,16}, hh {32,16}, mid {16}; lo {0,8}, hi {16,8}, mid {8}
+            case 0: xor16_at64<0>(t, r); xor16_at64<8>(t, r); xor16_at64<16>(t, r); xor16_at64<24>(t, r); break;
+            case 1: xor16_at64<16>(t, r); xor16_at64<8>(t, r); xor16_at64<32>(t, r); xor16_at64<24>(t, r); break;
+            case 2: xor16_at64<8>(t, r); xor16_at64<24>(t, r); break;
+            case 3: xor16_at64<32>(t, r); xor16_at64<40>(t, r); xor16_at64<16>(t, r); xor16_at64<24>(t, r); break;
+            case 4: xor16_at64<48>(t, r); xor16_at64<40>(t, r); xor16_at64<32>(t, r); xor16_at64<24>(t, r); break;
+            case 5: xor16_at64<40>(t, r); xor16_at64<24>(t, r); break;
+            case 6: xor16_at64<16>(t, r); xor16_at64<24>(t, r); break;
+            case 7: xor16_at64<32>(t, r); xor16_at64<24>(t, r); break;
+            default: xor16_at64<24>(t, r); break;
+        }
+    }
+}
+
+// K4d  same thread-per-(value, product, chunk) scheme with 32-word chunks (mul32_acc).  An operand whose degree bound is
+// exactly 64 (w - 1) — every carry of the multiplier circuit: bounds are sums of multiples of 256 — is taken as its
+// w - 1 low words plus the single coefficient of X^(64 (w-1)), so that 2048-bit operands are 2 chunks and not 3;
+// the coefficient's terms are word-aligned shifted XORs.
+struct ThreadMulShape {
+    uint32_t nx, ny; // 32-bit words of the low parts
+    bool xt, yt;     // operand has the separate top coefficient
+    bool swapped;    // x is op.b
+};
+__host__ __device__ inline ThreadMulShape thread_mul_shape(const MulOp &op) {
+    ThreadMulShape s;
+    s.nx = 2 * op.a.w;
+    s.ny = 2 * op.b.w;
+    s.xt = op.a.w >= 2 && op.a.deg == (uint64_t)64 * (op.a.w - 1);
+    s.yt = op.b.w >= 2 && op.b.deg == (uint64_t)64 * (op.b.w - 1);
+    if (s.xt) s.nx -= 2;
+    if (s.yt) s.ny -= 2;
+    s.swapped = s.nx > s.ny;
+    if (s.swapped) {
+        const uint32_t tn = s.nx; s.nx = s.ny; s.ny = tn;
+        const bool tt = s.xt; s.xt = s.yt; s.yt = tt;
+    }
+    return s;
+}
+
+static __global__ void __launch_bounds__(128, 4) mul_thread32_kernel(const MulOp *__restrict__ ops, uint64_t n, uint32_t *__restrict__ scratch) {
+    const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    // CTAs are dispatched x-fastest, z-slowest: walk products and chunks backwards so that the long threads (high chunks
+    // exist only for the big products, which come last in a column) start first and the short ones fill the tail
+    const MulOp op = ops[gridDim.y - 1 - blockIdx.y];
+    const uint32_t xi = gridDim.z - 1 - blockIdx.z;
+    const ThreadMulShape sh = thread_mul_shape(op);
+    if (32 * xi >= sh.nx) return;
+    const View &vx = sh.swapped ? op.b : op.a, &vy = sh.swapped ? op.a : op.b;
+    const uint32_t *gx = reinterpret_cast<const uint32_t *>(vx.base + v * vx.stride + vx.off);
+    const uint32_t *gy = reinterpret_cast<const uint32_t *>(vy.base + v * vy.stride + vy.off);
+    const uint32_t nx = sh.nx, ny = sh.ny;
+    const uint32_t xtop = sh.xt ? (gx[nx] & 1u) : 0u, ytop = sh.yt ? (gy[ny] & 1u) : 0u;
+    const uint64_t slot = ((uint64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    uint32_t *mbuf = scratch + slot * ADT_THREAD_WORDS, *tmp = mbuf + 32;
+    for (uint32_t i = 0; i < 32; ++i) mbuf[i] = (32 * xi + i < nx) ? gx[32 * xi + i] : 0u;
+    uint32_t *go = reinterpret_cast<uint32_t *>(op.o.base + v * op.o.stride + op.o.off);
+    const uint32_t no = 2 * op.o.w;
+    const uint32_t nyc = (ny + 31) / 32;
+    uint32_t t[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) t[i] = 0;
+    for (uint32_t j = 0; j <= nyc; ++j) {
+        if (j < nyc) {
+            const uint32_t *cp = gy + 32 * j;
+            if (32 * j + 32 > ny) {
+                for (uint32_t i = 0; i < 32; ++i) tmp[i] = (32 * j + i < ny) ? gy[32 * j + i] : 0u;
+                cp = tmp;
+            }
+            mul32_acc(mbuf, cp, t);
+            if (xi == 0 && xtop) { // X^(32 nx) * y: chunk j of y lands nx words up
+                for (uint32_t i = 0; i < 32; ++i) {
+                    const uint32_t w = cp[i];
+                    if (w && nx + 32 * j + i < no) atomicXor(go + nx + 32 * j + i, w);
+                }
+            }
+        }
+        const uint32_t w0 = 32 * (xi + j);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (t[i] && w0 + i < no) atomicXor(go + w0 + i, t[i]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            t[i] = t[32 + i];
+            t[32 + i] = 0;
+        }
+    }
+    if (ytop) { // X^(32 ny) * (this chunk of x)
+        for (uint32_t i = 0; i < 32; ++i) {
+            const uint32_t w = mbuf[i];
+            if (w && ny + 32 * xi + i < no) atomicXor(go + ny + 32 * xi + i, w);
+        }
+    }
+    if (xi == 0 && xtop && ytop && nx + ny < no) atomicXor(go + nx + ny, 1u);
 }
 
 // ----------------------------------------------------------------------------------------

@@ -84,7 +84,10 @@ uint64_t hm_context_kernel_launches(const hm_context *ctx);
 /* CUDA ordinal the context lives on. */
 int hm_context_device(const hm_context *ctx);
 /* Process-wide kernel-selection knobs (tests / experiments).  "adder_thread_min": smallest batch for which the
- * u32-class adder uses the thread-per-value Karatsuba kernel instead of the warp-per-value kernel (-1 = default). */
+ * u32-class adder uses the thread-per-value Karatsuba kernel instead of the warp-per-value kernel (-1 = default).
+ * "mul_thread_min": smallest (values x 24-word chunks) for which a general product uses the thread-per-chunk Karatsuba
+ * kernel (-1 = default).  "mul_circuit_sequential": 1 = launch the multiplier circuit's carry products one at a time
+ * instead of one batch per column (same polynomials; the A/B arm of a test). */
 int hm_set_tuning(const char *key, long value);
 
 /* Context::set_secret_key(SecretKey::from_bytes(bytes)) — src/context.rs:153-155, :568-571.

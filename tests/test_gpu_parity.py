@@ -403,14 +403,16 @@ def test_encrypt_seeded_device_masks(oracle, hm, params, dtype, n):
         np.testing.assert_array_equal(ctx.decrypt(ct), values)
 
 
-@pytest.mark.parametrize("force_thread", [False, True])
+@pytest.mark.parametrize("force_thread", [0, 24, 32])
 def test_poly_mul_random_shapes(oracle, hm, force_thread):
     """Randomised widths and degree bounds through every multiply kernel class (thread-per-product Karatsuba for the
     'k*256 + 1 bit' shapes; for the rest warp-cooperative tiles + scalar tail, or — forced here for small batches — the
-    thread-per-chunk Karatsuba kernel with atomic accumulation) against Polynomial::mul of the oracle."""
+    thread-per-chunk Karatsuba kernels with atomic accumulation, 24- and 32-word chunks) against Polynomial::mul of the
+    oracle."""
     rng = np.random.default_rng(2026)
     sk, pk, ctx = setup(oracle, hm, CONFIG_A, 2)
     hm.lib().hm_set_tuning(b"mul_thread_min", 0 if force_thread else 1 << 50)
+    hm.lib().hm_set_tuning(b"mul_thread_chunk", force_thread or 32)
     shapes = [(256, 256), (512, 512), (512, 1024), (1024, 512), (1024, 1024), (256, 512), (2048, 1024)]
     for _ in range(25):
         shapes.append((int(rng.integers(0, 3000)), int(rng.integers(0, 3000))))
@@ -434,6 +436,40 @@ def test_poly_mul_random_shapes(oracle, hm, force_thread):
             wantr = oracle.poly_binop(oracle.POLY_REM, want, sk)
             np.testing.assert_array_equal(rem.to_host(), expected_padded(wantr, n, rem.slot_words()), err_msg=f"rem da={da} db={db}")
     hm.lib().hm_set_tuning(b"mul_thread_min", -1)
+    hm.lib().hm_set_tuning(b"mul_thread_chunk", 32)
+
+
+@pytest.mark.parametrize("force_thread", [0, 24, 32])
+def test_mul_circuit_plans_agree(oracle, hm, force_thread):
+    """The column-batched multiplier circuit (prefix XORs + one batch of carry products per column) against the
+    one-product-at-a-time plan and against the oracle's mul_unsigned_internal (common.rs:66-105), bit for bit, with the
+    warp-cooperative and (forced) the thread-per-chunk Karatsuba product kernels."""
+    rng = np.random.default_rng(31)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 12)
+    lib = hm.lib()
+    n, L = 37, 8
+    a = rng.integers(0, 256, size=n, dtype=np.uint8)
+    b = rng.integers(0, 256, size=n, dtype=np.uint8)
+    a[:3] = [0, 255, 1]
+    b[:3] = [77, 255, 0]
+    ma, mb = masks_for(rng, n, L, CONFIG_A[3]), masks_for(rng, n, L, CONFIG_A[3])
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    try:
+        lib.hm_set_tuning(b"mul_thread_min", 0 if force_thread else 1 << 50)
+        lib.hm_set_tuning(b"mul_thread_chunk", force_thread or 32)
+        assert lib.hm_set_tuning(b"mul_circuit_sequential", 1) == 0
+        seq = ctx.apply2(hm.HomomorphicMultiplication, ca, cb).to_host()
+        assert lib.hm_set_tuning(b"mul_circuit_sequential", 0) == 0
+        r = ctx.apply2(hm.HomomorphicMultiplication, ca, cb)
+    finally:
+        lib.hm_set_tuning(b"mul_thread_min", -1)
+        lib.hm_set_tuning(b"mul_thread_chunk", 32)
+        lib.hm_set_tuning(b"mul_circuit_sequential", 0)
+    np.testing.assert_array_equal(r.to_host(), seq)
+    oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
+    want, _ = oracle.apply(oracle.OP_MUL, oa, ob, L, threads=oracle.max_threads())
+    np.testing.assert_array_equal(r.to_host(), expected_padded(want, n, r.slot_words()))
+    np.testing.assert_array_equal(ctx.decrypt(r), a * b)
 
 
 def test_empty_batches(oracle, hm):
