@@ -30,7 +30,8 @@ cudaError_t launch_mulrem_fresh_b(const uint64_t *A, const uint64_t *B, uint64_t
 static long g_adder_thread_min = -1;
 static long g_mul_thread_min = -1; // minimum (values x chunks) for the thread-per-chunk multiply; < 0 = default (128 per SM)
 static long g_mul_thread_chunk = 32; // 24 = the first thread-per-chunk kernel (3-way Karatsuba chunks)
-static long g_mul_circuit_seq = 0;  // 1 = launch the multiplier circuit's carry products one by one (the first plan)
+static long g_mul_circuit_seq = 0;
+static long g_adder_generic_seq = 0; // 1 = the generic adder evaluates the reference's formula literally (two long products per bit)  // 1 = launch the multiplier circuit's carry products one by one (the first plan)
 
 using hmk::Layout;
 using hmk::MulOp;
@@ -647,6 +648,10 @@ int hm_set_tuning(const char *key, long value) {
     if (strcmp(key, "mul_thread_chunk") == 0) {
         if (value != 24 && value != 32) return HM_ERR_INVALID_ARGUMENT;
         g_mul_thread_chunk = value;
+        return HM_OK;
+    }
+    if (strcmp(key, "adder_generic_sequential") == 0) {
+        g_adder_generic_seq = value;
         return HM_OK;
     }
     if (strcmp(key, "mul_circuit_sequential") == 0) {
@@ -1318,7 +1323,7 @@ int hm_result_slot_words(const hm_context *ctx, int op, uint32_t L, const uint32
 }
 
 // generic ripple-carry adder from views (any parameters / any input widths), reference order
-static int add_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
+static int add_generic_seq(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
     const uint32_t L = a->L;
     const size_t n = a->n;
     // arena per value: p, carry(2 buffers), cpp, cpp1, g, t — all at the final (largest) width
@@ -1393,6 +1398,121 @@ static int add_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
         rc = launch_xor_views(ctx, buf(nxt, dt), cpp, t, n); // carry = c_p1_p2.xor(...)
         cur = nxt;
         dc = dt;
+    }
+    cudaFreeAsync(arena, ctx->stream);
+    return rc;
+}
+
+// one launch for a list of slot XORs (o = a ^ b per entry)
+static int launch_xor_ops(hm_context *ctx, const std::vector<MulOp> &ops, size_t n) {
+    if (ops.empty() || n == 0) return HM_OK;
+    if (ops.size() > 65535) return HM_ERR_UNSUPPORTED;
+    size_t slot = 0;
+    int rc = ensure_ops(ctx, ops.size(), &slot);
+    if (rc != HM_OK) return rc;
+    memcpy(ctx->h_ops + slot, ops.data(), ops.size() * sizeof(MulOp));
+    CK(cudaMemcpyAsync(ctx->d_ops + slot, ctx->h_ops + slot, ops.size() * sizeof(MulOp), cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t wmax = 1;
+    for (const MulOp &op : ops) wmax = std::max(wmax, op.o.w);
+    const int per_op = std::max(1, grid_for(ctx, (uint64_t)n * wmax, 256, 16) / (int)std::min<size_t>(ops.size(), 16));
+    const dim3 grid((unsigned)per_op, (unsigned)ops.size());
+    hmk::xor_ops_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_ops + slot, n);
+    return post_launch(ctx, "xor_ops_kernel");
+}
+
+// Regrouped plan of the same ripple-carry circuit for any degree bounds (the fused kernels cover D in {128, 256}).
+// The reference computes carry' = cpp + g (cpp + 1) with cpp = p carry (common.rs:44-53), two long products per bit;
+// expanded over GF(2) that is carry' = (p + g p) carry + g = m carry + g, the form the fused kernels use: the same
+// polynomial, one long product per bit.  All p_k, g_k, m_k are independent of the chain and are produced by three batched
+// launches; the chain itself is one product + one XOR per bit, written straight into the output slots (s_k = c_k + p_k
+// is completed by one batched XOR at the end).
+static int add_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
+    if (g_adder_generic_seq) return add_generic_seq(ctx, a, b, o);
+    const uint32_t L = a->L;
+    const size_t n = a->n;
+    std::vector<uint64_t> dp(L), dg(L), dm(L);
+    std::vector<uint64_t> offP(L), offG(L), offM(L);
+    uint64_t cursor = 0;
+    for (uint32_t k = 0; k < L; ++k) {
+        dp[k] = std::max(a->degb[k], b->degb[k]);
+        dg[k] = a->degb[k] + b->degb[k];
+        dm[k] = dg[k] + dp[k];
+        offP[k] = cursor; cursor += dp[k] / 64 + 1;
+        offG[k] = cursor; cursor += dg[k] / 64 + 1;
+        offM[k] = cursor; cursor += dm[k] / 64 + 1;
+    }
+    const size_t arena_words = cursor;
+    if (arena_words >> 32) return HM_ERR_UNSUPPORTED;
+    uint64_t *arena = nullptr;
+    CK(cudaMallocAsync(&arena, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
+    // products may be accumulated with atomics (thread-per-chunk kernel): clear their destinations once
+    CK(cudaMemsetAsync(arena, 0, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
+    CK(cudaMemsetAsync(o->d, 0, std::max<size_t>(n * o->value_words * 8, 16), ctx->stream));
+    auto aview = [&](uint64_t off, uint64_t degb) {
+        View v;
+        v.base = arena;
+        v.stride = arena_words;
+        v.off = (uint32_t)off;
+        v.w = (uint32_t)(degb / 64 + 1);
+        v.deg = degb;
+        return v;
+    };
+    int rc = HM_OK;
+    std::vector<MulOp> ops;
+    for (uint32_t k = 0; k < L; ++k) ops.push_back(MulOp{slot_view(a, k), slot_view(b, k), aview(offP[k], dp[k])}); // p = a + b
+    rc = launch_xor_ops(ctx, ops, n);
+    if (rc == HM_OK && L >= 2) {
+        ops.clear();
+        for (uint32_t k = 0; k + 1 < L; ++k) ops.push_back(MulOp{slot_view(a, k), slot_view(b, k), aview(offG[k], dg[k])}); // g = a b
+        rc = launch_mul_ops(ctx, ops, n, true);
+    }
+    if (rc == HM_OK && L >= 3) {
+        ops.clear();
+        for (uint32_t k = 1; k + 1 < L; ++k) ops.push_back(MulOp{aview(offG[k], dg[k]), aview(offP[k], dp[k]), aview(offM[k], dm[k])}); // g p
+        rc = launch_mul_ops(ctx, ops, n, true);
+        if (rc == HM_OK) {
+            ops.clear();
+            for (uint32_t k = 1; k + 1 < L; ++k) ops.push_back(MulOp{aview(offM[k], dm[k]), aview(offP[k], dp[k]), aview(offM[k], dm[k])}); // m = g p + p
+            rc = launch_xor_ops(ctx, ops, n);
+        }
+    }
+    // chain: slot k+1 <- c_{k+1} = m_k c_k + g_k   (c_1 = g_0)
+    uint64_t dc = 0;
+    std::vector<MulOp> one(1);
+    for (uint32_t k = 0; k + 1 < L && rc == HM_OK; ++k) {
+        View dst = slot_view(o, k + 1);
+        if (k == 0) {
+            dc = dg[0];
+        } else {
+            View ck = slot_view(o, k);
+            ck.w = (uint32_t)(dc / 64 + 1);
+            ck.deg = dc;
+            dc = dm[k] + dc;
+            View ok = dst;
+            ok.w = (uint32_t)std::min<uint64_t>(dst.w, dc / 64 + 1);
+            ok.deg = dc;
+            one[0] = MulOp{aview(offM[k], dm[k]), ck, ok};
+            rc = launch_mul_ops(ctx, one, n, true);
+            if (rc != HM_OK) break;
+        }
+        if (dc > o->degb[k + 1]) { // cannot happen: result_bounds follows the same recurrence
+            rc = HM_ERR_UNSUPPORTED;
+            break;
+        }
+        View gk = aview(offG[k], dg[k]);
+        View og = dst;
+        og.w = std::min(dst.w, gk.w);
+        rc = launch_xor_views(ctx, og, og, gk, n); // + g_k over g_k's width
+    }
+    if (rc == HM_OK) { // s_k = c_k + p_k
+        ops.clear();
+        for (uint32_t k = 0; k < L; ++k) {
+            View pk = aview(offP[k], dp[k]);
+            View ok = slot_view(o, k);
+            ok.w = std::min(ok.w, pk.w);
+            ops.push_back(MulOp{ok, pk, ok});
+        }
+        rc = launch_xor_ops(ctx, ops, n);
     }
     cudaFreeAsync(arena, ctx->stream);
     return rc;

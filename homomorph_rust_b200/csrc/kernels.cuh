@@ -543,6 +543,21 @@ static __global__ void __launch_bounds__(256) xor_views_kernel(View o, View a, V
     }
 }
 
+// Batched form of xor_views_kernel: ops[blockIdx.y].o = ops[..].a ^ ops[..].b (b may be a null view; o may alias a).
+static __global__ void __launch_bounds__(256) xor_ops_kernel(const MulOp *__restrict__ ops, uint64_t n) {
+    const MulOp op = ops[blockIdx.y];
+    const View o = op.o, a = op.a, b = op.b;
+    const uint64_t total = n * o.w;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = i / o.w;
+        const uint32_t j = (uint32_t)(i % o.w);
+        uint64_t x = 0;
+        if (j < a.w) x ^= a.base[v * a.stride + a.off + j];
+        if (b.base && j < b.w) x ^= b.base[v * b.stride + b.off + j];
+        o.base[v * o.stride + o.off + j] = x;
+    }
+}
+
 // Running XOR over a list of slots: ops[t].a is the t-th item x_t, ops[t].o (when its base is not null) receives the
 // prefix x_0 ^ ... ^ x_t.  One thread per (value, word); `width` is the widest destination.  Used by the multiplier
 // circuit (reference src/impls/numbers/common.rs:78-101): the carries of one column are x_t * (x_0 ^ ... ^ x_{t-1}),

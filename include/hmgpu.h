@@ -87,7 +87,9 @@ int hm_context_device(const hm_context *ctx);
  * u32-class adder uses the thread-per-value Karatsuba kernel instead of the warp-per-value kernel (-1 = default).
  * "mul_thread_min": smallest (values x 24-word chunks) for which a general product uses the thread-per-chunk Karatsuba
  * kernel (-1 = default).  "mul_circuit_sequential": 1 = launch the multiplier circuit's carry products one at a time
- * instead of one batch per column (same polynomials; the A/B arm of a test). */
+ * instead of one batch per column; "adder_generic_sequential": 1 = the generic adder evaluates common.rs:44-53 literally
+ * (two long products per bit) instead of the regrouped one-product-per-bit form; "mul_thread_chunk": 24 | 32 words per
+ * chunk of the thread-per-chunk product kernel.  All of them give the same polynomials: they are the A/B arms of tests. */
 int hm_set_tuning(const char *key, long value);
 
 /* Context::set_secret_key(SecretKey::from_bytes(bytes)) — src/context.rs:153-155, :568-571.

@@ -439,6 +439,38 @@ def test_poly_mul_random_shapes(oracle, hm, force_thread):
     hm.lib().hm_set_tuning(b"mul_thread_chunk", 32)
 
 
+@pytest.mark.parametrize("params,dtype,n,force_thread", [((256, 256, 1, 64), np.uint8, 9, 0), ((256, 256, 1, 64), np.uint16, 5, 32), (CONFIG_B, np.uint8, 4, 32), ((64, 16, 1, 16), np.uint16, 6, 24), (CONFIG_A, np.uint32, 3, 32)])
+def test_add_generic_plans_agree(oracle, hm, params, dtype, n, force_thread):
+    """The regrouped generic adder (batched p, g, m = p + g p, then one product per bit) against the literal evaluation
+    of common.rs:44-53 (two long products per bit) and against the oracle, with the warp-cooperative and (forced) the
+    thread-per-chunk product kernels."""
+    rng = np.random.default_rng(n * 7 + params[0])
+    sk, pk, ctx = setup(oracle, hm, params, 17)
+    lib = hm.lib()
+    L = np.dtype(dtype).itemsize * 8
+    a = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    b = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    a[:2], b[:2] = [0, np.iinfo(dtype).max], [0, 1]
+    ma, mb = masks_for(rng, n, L, params[3]), masks_for(rng, n, L, params[3])
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    try:
+        lib.hm_set_tuning(b"mul_thread_min", 0 if force_thread else 1 << 50)
+        lib.hm_set_tuning(b"mul_thread_chunk", force_thread or 32)
+        assert lib.hm_set_tuning(b"adder_generic_sequential", 1) == 0
+        seq = ctx.apply2(hm.HomomorphicAddition, ca, cb, generic=True).to_host()
+        assert lib.hm_set_tuning(b"adder_generic_sequential", 0) == 0
+        r = ctx.apply2(hm.HomomorphicAddition, ca, cb, generic=True)
+    finally:
+        lib.hm_set_tuning(b"mul_thread_min", -1)
+        lib.hm_set_tuning(b"mul_thread_chunk", 32)
+        lib.hm_set_tuning(b"adder_generic_sequential", 0)
+    np.testing.assert_array_equal(r.to_host(), seq)
+    oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
+    want, _ = oracle.apply(oracle.OP_ADD, oa, ob, L, threads=oracle.max_threads())
+    np.testing.assert_array_equal(r.to_host(), expected_padded(want, n, r.slot_words()))
+    np.testing.assert_array_equal(ctx.decrypt(r), a + b)
+
+
 @pytest.mark.parametrize("force_thread", [0, 24, 32])
 def test_mul_circuit_plans_agree(oracle, hm, force_thread):
     """The column-batched multiplier circuit (prefix XORs + one batch of carry products per column) against the
