@@ -44,7 +44,7 @@ BITMACS_PER_MULREM = 66049 + 49665
 BYTES_PER_MULREM = 96
 # dram__bytes_read.sum + dram__bytes_write.sum of adder_fused_kernel from the ncu --set full capture in profiles/
 # (r01_adder_ncu_details.txt: 42.3 MB + 711.4 MB for 16 384 adds), per add
-NCU_DRAM_BYTES_PER_ADD = (4.891079e9 + 5.466964e9) / 75776  # ncu capture of adder_thread_kernel<4>, profiles/r01_adder_thread_ncu_details.txt
+NCU_DRAM_BYTES_PER_ADD = (4.277474e9 + 4.852116e9) / 75776  # ncu capture of adder_thread_smem_kernel<4>, profiles/r01_adder_thread_smem_ncu_details.txt
 
 
 def measured_peaks():
@@ -471,12 +471,12 @@ def run_ours(args, rank, local_rank, world):
         k8_ach = n * KARA8_PER_ADD / launch_s
         # The binding unit of this kernel is the integer multiplier (FMA-heavy pipe): the adder is a chain of 8x8-word
         # Karatsuba products, 432 IMAD.WIDE each.  frac = products/s achieved / the same product timed in isolation.
-        roofline = {"kernel": "adder_thread_kernel<4> (thread-per-value Karatsuba on IMAD.WIDE + LOP3)", "bound": "alu",
+        roofline = {"kernel": "adder_thread_smem_kernel<4> (thread-per-value Karatsuba on IMAD.WIDE + LOP3, operands staged in shared memory by cp.async)", "bound": "alu",
                     "bound_detail": "fma-heavy pipe (integer multiplier): 432 IMAD.WIDE per 8x8-word Karatsuba product, 2 881 products per add",
                     "achieved": k8_ach / 1e9, "peak": k8.value / 1e9, "unit": "G 8x8-word products/s", "frac": k8_ach / k8.value, "traffic": None,
                     "peak_source": "measured in this run: hm_measure_kara8_peak (the product in isolation, 16 warps/SM)",
-                    "pipes_busy_ncu": {"alu": 0.55, "fmaheavy": 0.55, "issue_slots": 0.43,
-                                       "source": "profiles/r01_adder_thread_ncu_details.txt (75 776 adds)"},
+                    "pipes_busy_ncu": {"alu": 0.58, "fmaheavy": 0.58, "issue_slots": 0.46,
+                                       "source": "profiles/r01_adder_thread_smem_ncu_details.txt (75 776 adds)"},
                     "lop3_equivalent": {"achieved": ach / 1e12, "peak": peak_bitmac / 1e12, "unit": "Tbit-MAC/s", "frac": ach / peak_bitmac,
                                         "peak_source": f"measured in this run: LOP3 issue-rate probe, {lane_ops.value / 1e12:.2f} T lane-ops/s at ~{mhz.value:.0f} MHz (x32 bits)",
                                         "note": "the reference's schoolbook AND-XOR pairs (SURVEY.md A.2) against the LOP3-only issue rate, the "
@@ -485,9 +485,9 @@ def run_ours(args, rank, local_rank, world):
         roofline["product_pipe"] = {k: roofline[k] for k in ("achieved", "peak", "unit", "frac", "peak_source")}  # earlier name of the same figures
         hbm_peak, src = measured_peaks()
         gbs = n * BYTES_PER_ADD / launch_s / 1e9
-        roofline_hbm = {"kernel": "adder_thread_kernel<4>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+        roofline_hbm = {"kernel": "adder_thread_smem_kernel<4>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                         "frac": gbs / hbm_peak, "traffic": (n * NCU_DRAM_BYTES_PER_ADD) if NCU_DRAM_BYTES_PER_ADD else None,
-                        "traffic_source": "ncu --set full capture (profiles/r01_adder_thread_ncu_details.txt), scaled per add; "
+                        "traffic_source": "ncu --set full capture (profiles/r01_adder_thread_smem_ncu_details.txt), scaled per add; "
                                           "algorithmic bytes per launch = %d" % (n * BYTES_PER_ADD),
                         "peak_source": src}
 
@@ -562,7 +562,7 @@ def run_ours(args, rank, local_rank, world):
                     "pairs_per_step": ne, "steps": e2e_steps, "step_ms": e2e_step_ms, "call": "hm_apply2_host (pinned host ciphertexts in/out, 3-stream chunked pipeline)",
                     "matches_device_result": e2e_matches},
             "gpu_launches": int(l_after - l_before),
-            "kernels_in_step": ["adder_thread_kernel<4>"],
+            "kernels_in_step": ["adder_thread_smem_kernel<4>"],
             "clocks": clocks,
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "cpu_baseline": cpu,

@@ -1848,6 +1848,15 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                 if (mode >= 3 && wd == 8 && n >= (g_adder_thread_min >= 0 ? (size_t)g_adder_thread_min : (size_t)ctx->sm_count * 256)) { // thread-per-value Karatsuba chain; mode - 1 = CTAs per SM
                     const int per_sm = mode - 1;
                     const int blocks = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->sm_count * per_sm);
+                    static const int use_smem = getenv("HM_ADDER_SMEM") ? atoi(getenv("HM_ADDER_SMEM")) : 1; // 0 = first thread kernel (scratch in global memory)
+                    if (use_smem && (per_sm == 3 || per_sm == 4)) { // working set in shared memory, chunks prefetched by cp.async
+                        auto sk = per_sm == 3 ? hmk::adder_thread_smem_kernel<3> : hmk::adder_thread_smem_kernel<4>;
+                        CK(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, hmk::ADS_SMEM_BYTES));
+                        CK(cudaFuncSetAttribute(sk, cudaFuncAttributePreferredSharedMemoryCarveout, use_smem > 1 ? use_smem : 70));
+                        sk<<<blocks, 128, hmk::ADS_SMEM_BYTES, ctx->stream>>>(a->d, b->d, o->d, n, a->L, make_layout(o));
+                        rc = post_launch(ctx, "adder_thread_smem_kernel");
+                        break;
+                    }
                     uint32_t *scratch = nullptr;
                     CK(cudaMallocAsync(&scratch, (size_t)blocks * 128 * hmk::ADT_THREAD_WORDS * 4, ctx->stream));
                     auto tk = per_sm == 2 ? hmk::adder_thread_kernel<2> : (per_sm == 3 ? hmk::adder_thread_kernel<3> : (per_sm == 4 ? hmk::adder_thread_kernel<4> : (per_sm == 5 ? hmk::adder_thread_kernel<5> : (per_sm == 6 ? hmk::adder_thread_kernel<6> : hmk::adder_thread_kernel<8>))));

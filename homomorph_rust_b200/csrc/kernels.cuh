@@ -12,14 +12,15 @@
 //   mask_fill_kernel (Philox4x32-10)               CipheredBit::part       src/cipher.rs:92-97 (seeded replacement)
 //   decrypt_uniform / decrypt_value_tma / decrypt_slots   CipheredBit::decipher   src/cipher.rs:119-122 (+ packing :227-237)
 //   xor_* / not_kernel                             Polynomial::add, gate_xor/not   src/polynomial.rs:190-243, common.rs:21-35
-//   mul_small / mul_thread / mul_warp / mul_views  Polynomial::mul         src/polynomial.rs:252-310
+//   mul_small / mul_thread32 / mul_thread / mul_warp / mul_views   Polynomial::mul   src/polynomial.rs:252-310
 //   rem_fold / rem_generic                         Polynomial::rem         src/polynomial.rs:316-365
 //   mulrem_fresh_kernel                            mul followed by rem (the BASELINE "mul+rem" unit)
-//   adder_thread_kernel / adder_fused_kernel       add_internal            src/impls/numbers/common.rs:37-56
-//   (mul_unsigned_internal, common.rs:66-105, is a host-planned sequence of the multiply / xor kernels: hmgpu.cu)
+//   adder_thread_smem / adder_thread / adder_fused  add_internal           src/impls/numbers/common.rs:37-56
+//   prefix_xor_kernel / xor_ops_kernel             the XOR halves of mul_unsigned_internal (common.rs:66-105) and of the
+//                                                  generic adder; both circuits are host-planned batches of launches: hmgpu.cu
 //
 // Building blocks: clmul32_imad (32x32 carry-less product on the integer multiplier), clmul_kara<N> (Karatsuba over
-// words), mul24_acc (24x24-word product as six 8x8-word Karatsubas), clmul_regs (shift/mask schoolbook, ALU only),
+// words), mul24_acc / mul32_acc (24x24- / 32x32-word products as six / nine 8x8-word Karatsubas), clmul_regs (shift/mask schoolbook, ALU only),
 // fold_word (CRC-style remainder step), TMA 1-D bulk copy + mbarrier helpers.
 #pragma once
 #include <cuda_runtime.h>
@@ -1594,6 +1595,209 @@ __global__ void __launch_bounds__(128, MINB) adder_thread_kernel(const uint64_t 
                 }
             }
             len += 3 * WD; // deg c_{k+1} = deg c_k + 3D
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// K6c  the same thread-per-value chain with its working set in shared memory: m_k and a double-buffered 24-word chunk
+// of c_k live in a [word pair][thread] array (one 8-byte column per thread: conflict-free LDS.64/STS.64), and chunk j+1
+// is fetched from the result slot with cp.async (LDGSTS, no registers) while chunk j is being multiplied, so the
+// global-memory latency of the operand reads is off the critical path of the four resident warps per scheduler.
+// ----------------------------------------------------------------------------------------
+constexpr int ADS_PAIRS = 36;                          // 12 (m_k) + 2 x 12 (chunk double buffer) uint2 per thread
+constexpr int ADS_SMEM_BYTES = ADS_PAIRS * 128 * 8;    // per 128-thread CTA
+
+// t ^= m * c, both operands in the interleaved shared layout (pair q of this thread at base[q * 128])
+__device__ __forceinline__ void mul24_acc_s(const uint2 *__restrict__ m, const uint2 *__restrict__ c, uint32_t (&t)[48]) {
+    auto blk = [](uint32_t (&dst)[8], const uint2 *src) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint2 w = src[q * 128];
+            dst[2 * q] = w.x;
+            dst[2 * q + 1] = w.y;
+        }
+    };
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+        const int o1 = (i < 3) ? 4 * i : (i == 5 ? 4 : 0); // in pairs
+        const int o2 = (i < 3) ? -1 : (i == 3 ? 4 : 8);
+        uint32_t x[8], y[8], r[16];
+        blk(x, m + o1 * 128);
+        blk(y, c + o1 * 128);
+        if (o2 >= 0) {
+            uint32_t u[8], w[8];
+            blk(u, m + o2 * 128);
+            blk(w, c + o2 * 128);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                x[q] ^= u[q];
+                y[q] ^= w[q];
+            }
+        }
+        clmul_kara<8>(x, y, r);
+        switch (i) {
+            case 0: xor16_at<0>(t, r); xor16_at<8>(t, r); xor16_at<16>(t, r); break;
+            case 1: xor16_at<16>(t, r); xor16_at<8>(t, r); xor16_at<24>(t, r); break;
+            case 2: xor16_at<32>(t, r); xor16_at<16>(t, r); xor16_at<24>(t, r); break;
+            case 3: xor16_at<8>(t, r); break;
+            case 4: xor16_at<16>(t, r); break;
+            default: xor16_at<24>(t, r); break;
+        }
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) adder_thread_smem_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
+                                                                   uint64_t *__restrict__ O, uint64_t n, uint32_t L, Layout lo) {
+    constexpr int WD = 8, WF = 5;
+    extern __shared__ __align__(16) uint2 ads_smem[];
+    uint2 *mb = ads_smem + threadIdx.x, *cb0 = mb + 12 * 128, *cb1 = mb + 24 * 128;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t v = tid; v < n; v += nthreads) {
+        const uint64_t *Av = A + v * (uint64_t)L * WF, *Bv = B + v * (uint64_t)L * WF;
+        uint32_t *Ov = reinterpret_cast<uint32_t *>(O + v * (uint64_t)lo.value_words);
+        uint32_t len = 0; // words of c_k (c_0 = 0)
+        for (uint32_t k = 0; k < L; ++k) {
+            uint32_t a[WD], b[WD], p[WD + 1];
+#pragma unroll
+            for (int j = 0; j < WD / 2; ++j) {
+                const uint64_t x = __ldg(Av + (size_t)k * WF + j), y = __ldg(Bv + (size_t)k * WF + j);
+                a[2 * j] = (uint32_t)x; a[2 * j + 1] = (uint32_t)(x >> 32);
+                b[2 * j] = (uint32_t)y; b[2 * j + 1] = (uint32_t)(y >> 32);
+            }
+            const uint32_t atop = (uint32_t)__ldg(Av + (size_t)k * WF + WD / 2) & 1u, btop = (uint32_t)__ldg(Bv + (size_t)k * WF + WD / 2) & 1u;
+#pragma unroll
+            for (int j = 0; j < WD; ++j) p[j] = a[j] ^ b[j];
+            const uint32_t ptop = atop ^ btop;
+            p[WD] = ptop;
+            if (k == 0) { // s_0 = p_0
+                uint32_t *dst = Ov + 2 * lo.off[0];
+                const uint32_t wo = 2 * (lo.off[1] - lo.off[0]);
+#pragma unroll
+                for (int j = 0; j <= WD; ++j) dst[j] = p[j];
+                for (uint32_t j = WD + 1; j < wo; ++j) dst[j] = 0;
+            }
+            if (k + 1 == L) break;
+            uint32_t g[2 * WD];
+            kara8_call(a, b, g);
+            const uint32_t ma = 0u - atop, mbm = 0u - btop;
+#pragma unroll
+            for (int j = 0; j < WD; ++j) g[WD + j] ^= (b[j] & ma) ^ (a[j] & mbm);
+            const uint32_t gtop = atop & btop;
+            uint32_t pn[WD + 1];
+#pragma unroll
+            for (int j = 0; j < WD / 2; ++j) {
+                const uint64_t x = __ldg(Av + (size_t)(k + 1) * WF + j) ^ __ldg(Bv + (size_t)(k + 1) * WF + j);
+                pn[2 * j] = (uint32_t)x; pn[2 * j + 1] = (uint32_t)(x >> 32);
+            }
+            pn[WD] = (uint32_t)(__ldg(Av + (size_t)(k + 1) * WF + WD / 2) ^ __ldg(Bv + (size_t)(k + 1) * WF + WD / 2)) & 1u;
+            uint32_t *sdst = Ov + 2 * lo.off[k + 1];
+            const uint32_t swo = 2 * (lo.off[k + 2] - lo.off[k + 1]);
+            if (k == 0) { // c_1 = g_0
+#pragma unroll
+                for (int j = 0; j < 2 * WD; ++j) sdst[j] = g[j] ^ (j <= WD ? pn[j] : 0u);
+                sdst[2 * WD] = gtop;
+                for (uint32_t j = 2 * WD + 1; j < swo; ++j) sdst[j] = 0;
+                len = 2 * WD + 1;
+                continue;
+            }
+            { // m = p + g * p : 24 low words into shared memory + the coefficient of X^768
+                uint32_t m[24], glo[WD], ghi[WD], q0[2 * WD], q1[2 * WD];
+#pragma unroll
+                for (int j = 0; j < WD; ++j) { glo[j] = g[j]; ghi[j] = g[WD + j]; }
+                kara8_call(glo, p, q0);
+                kara8_call(ghi, p, q1);
+#pragma unroll
+                for (int j = 0; j < WD; ++j) {
+                    m[j] = q0[j] ^ p[j];
+                    m[WD + j] = q0[WD + j] ^ q1[j];
+                    m[2 * WD + j] = q1[WD + j];
+                }
+                const uint32_t mp = 0u - ptop, mg = 0u - gtop;
+#pragma unroll
+                for (int j = 0; j < 2 * WD; ++j) m[WD + j] ^= g[j] & mp;
+#pragma unroll
+                for (int j = 0; j < WD; ++j) m[2 * WD + j] ^= p[j] & mg;
+                m[WD] ^= ptop;
+#pragma unroll
+                for (int q = 0; q < 12; ++q) mb[q * 128] = make_uint2(m[2 * q], m[2 * q + 1]);
+            }
+            const uint32_t mtop = gtop & ptop;
+            const uint32_t *cslot = Ov + 2 * lo.off[k]; // s_k = c_k + p_k
+            const uint32_t nchunks = (len + 23) / 24;
+            // first chunk (p_k mixed in) and a ragged last chunk are staged by hand; full chunks come by cp.async
+            auto fill_sync = [&](uint2 *dstb, uint32_t j) {
+                for (uint32_t q = 0; q < 12; ++q) {
+                    uint32_t v2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t w = 24 * j + 2 * q + h;
+                        uint32_t val = (w < len) ? cslot[w] : 0u;
+                        if (w <= (uint32_t)WD) {
+                            uint32_t pw = p[0];
+#pragma unroll
+                            for (int qq = 1; qq <= WD; ++qq) pw = (w == (uint32_t)qq) ? p[qq] : pw;
+                            val ^= pw;
+                        }
+                        v2[h] = val;
+                    }
+                    dstb[q * 128] = make_uint2(v2[0], v2[1]);
+                }
+            };
+            auto fill_async = [&](uint2 *dstb, uint32_t j) {
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dstb);
+                const uint32_t *src = cslot + 24 * j;
+#pragma unroll
+                for (int q = 0; q < 12; ++q)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + q * 128 * 8), "l"(src + 2 * q) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            fill_sync(cb0, 0);
+            uint32_t t[48];
+#pragma unroll
+            for (int i = 0; i < 48; ++i) t[i] = 0;
+            for (uint32_t j = 0; j <= nchunks; ++j) {
+                uint2 *cur = (j & 1) ? cb1 : cb0, *nxt = (j & 1) ? cb0 : cb1;
+                if (j < nchunks) {
+                    bool pref = false;
+                    if (j + 1 < nchunks) {
+                        if (24 * (j + 1) + 24 <= len) {
+                            fill_async(nxt, j + 1);
+                            pref = true;
+                        } else {
+                            fill_sync(nxt, j + 1);
+                        }
+                    }
+                    if (pref) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    mul24_acc_s(mb, cur, t);
+                    if (mtop) { // X^768 * c: chunk j lands in chunk j+1
+#pragma unroll
+                        for (int q = 0; q < 12; ++q) {
+                            const uint2 w = cur[q * 128];
+                            t[24 + 2 * q] ^= w.x;
+                            t[24 + 2 * q + 1] ^= w.y;
+                        }
+                    }
+                }
+                if (j == 0) {
+#pragma unroll
+                    for (int i = 0; i < 2 * WD; ++i) t[i] ^= g[i];
+                    t[2 * WD] ^= gtop;
+#pragma unroll
+                    for (int i = 0; i <= WD; ++i) t[i] ^= pn[i];
+                }
+#pragma unroll
+                for (int q = 0; q < 12; ++q)
+                    if (24 * j + 2 * q < swo) *reinterpret_cast<uint2 *>(sdst + 24 * j + 2 * q) = make_uint2(t[2 * q], t[2 * q + 1]);
+#pragma unroll
+                for (int i = 0; i < 24; ++i) {
+                    t[i] = t[24 + i];
+                    t[24 + i] = 0;
+                }
+            }
+            len += 3 * WD;
         }
     }
 }
