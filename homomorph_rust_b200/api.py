@@ -309,6 +309,15 @@ class Ciphered:
         _check(self._ctx._h, N.lib().hm_batch_clone(self._ctx._h, self._h, C.byref(out)))
         return Ciphered(self._ctx, out.value)
 
+    def slice(self, first_bit: int, n_bits: int, dtype=None) -> "Ciphered":
+        """Slots [first_bit, first_bit + n_bits) of every value as their own batch: `split_at` + `new_from_raw` on one
+        field of a user struct (examples/simple_struct.rs:32-45)."""
+        out = C.c_void_p()
+        _check(self._ctx._h, N.lib().hm_batch_slice(self._ctx._h, self._h, first_bit, n_bits, C.byref(out)))
+        r = Ciphered(self._ctx, out.value)
+        r.dtype = np.dtype(dtype) if dtype is not None else None
+        return r
+
     def free(self) -> None:
         if self._h is not None and self._h.value:
             N.lib().hm_batch_free(self._ctx._h, self._h)
@@ -410,9 +419,15 @@ class Context:
         if self._pk is None:
             raise PublicKeyUnset("PublicKeyUnset")
         values = np.ascontiguousarray(values)
-        if values.dtype.kind not in "ui":
+        if values.dtype.kind == "V" and values.dtype.names:  # a struct of integers: fields in order, each little endian
+            if any(values.dtype[f].kind not in "ui" or values.dtype[f].byteorder == ">" for f in values.dtype.names) or \
+                    values.dtype.itemsize != sum(values.dtype[f].itemsize for f in values.dtype.names):
+                raise TypeError("packed structs of little-endian integers only (bincode fixint, src/cipher.rs:6-13)")
+            le = values
+        elif values.dtype.kind not in "ui":
             raise TypeError("integers only (bincode fixint little-endian, src/cipher.rs:6-13)")
-        le = values.astype(values.dtype.newbyteorder("<"), copy=False)
+        else:
+            le = values.astype(values.dtype.newbyteorder("<"), copy=False)
         n, L = values.size, values.dtype.itemsize * 8
         raw = np.frombuffer(le.tobytes(), dtype=np.uint8)
         if seed is not None:  # masks generated on the device from a counter-based PRNG; nothing but plaintext is uploaded
@@ -441,7 +456,10 @@ class Context:
             raise InvalidCipheredLength(f"InvalidCipheredLength {{ len: {L} }}")
         out = np.zeros(len(c) * (L // 8), dtype=np.uint8)
         _check(self._h, N.lib().hm_decrypt(self._h, c._h, out.ctypes.data))
-        dtype = dtype or getattr(c, "dtype", None) or np.dtype(f"<u{L // 8}")
+        dtype = dtype or getattr(c, "dtype", None)
+        if dtype is not None and np.dtype(dtype).kind == "V":
+            return out.view(np.dtype(dtype))
+        dtype = dtype or (np.dtype(f"<u{L // 8}") if L // 8 in (1, 2, 4, 8) else np.dtype((np.uint8, (L // 8,))))
         return out.view(np.dtype(dtype).newbyteorder("<")).astype(dtype)
 
     # -- operations -----------------------------------------------------------------------
@@ -462,6 +480,26 @@ class Context:
         out = C.c_void_p()
         fn = N.lib().hm_apply2_generic if generic else N.lib().hm_apply2
         _check(self._h, fn(self._h, op.code, a._h, b._h, C.byref(out)))
+        r = Ciphered(self, out.value)
+        r.dtype = getattr(a, "dtype", None)
+        return r
+
+    def concat(self, parts: Sequence[Ciphered], dtype=None) -> Ciphered:
+        """The `extend_from_slice` merge of per-field results (examples/simple_struct.rs:52-58)."""
+        arr = (C.c_void_p * len(parts))(*[p._h.value for p in parts])
+        out = C.c_void_p()
+        _check(self._h, N.lib().hm_batch_concat(self._h, arr, len(parts), C.byref(out)))
+        r = Ciphered(self, out.value)
+        r.dtype = np.dtype(dtype) if dtype is not None else None
+        return r
+
+    def apply2_fields(self, op, a: Ciphered, b: Ciphered, field_bits: Sequence[int]) -> Ciphered:
+        """An operation on every field of a struct at once: field f is `field_bits[f]` consecutive bits (the Vec3Add of
+        examples/simple_struct.rs with field_bits = [16, 16, 16])."""
+        self._validate(op)
+        fb = (C.c_uint32 * len(field_bits))(*[int(x) for x in field_bits])
+        out = C.c_void_p()
+        _check(self._h, N.lib().hm_apply2_fields(self._h, op.code, a._h, b._h, fb, len(field_bits), C.byref(out)))
         r = Ciphered(self, out.value)
         r.dtype = getattr(a, "dtype", None)
         return r

@@ -1933,6 +1933,87 @@ int hm_apply2(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_
     return apply2_impl(ctx, op, a, b, out);
 }
 
+// ---- struct fields: Ciphered<T>::split_at / new_from_raw / extend_from_slice, examples/simple_struct.rs:32-58 ----------
+int hm_batch_slice(hm_context *ctx, const hm_batch *src, uint32_t first_bit, uint32_t n_bits, hm_batch **out) {
+    if (!ctx || !src || !out || n_bits == 0) return HM_ERR_INVALID_ARGUMENT;
+    if ((uint64_t)first_bit + n_bits > src->L) return HM_ERR_INVALID_LENGTH; // split_at past the end panics in the reference
+    USE_DEV(ctx);
+    hm_batch *o = new_batch(ctx, src->n, n_bits, src->degb.data() + first_bit);
+    if (!o) return HM_ERR_INVALID_ARGUMENT;
+    int rc = alloc_batch(ctx, o);
+    if (rc != HM_OK) {
+        delete o;
+        return rc;
+    }
+    std::vector<MulOp> ops;
+    for (uint32_t k = 0; k < n_bits; ++k) ops.push_back(MulOp{slot_view(src, first_bit + k), null_view(), slot_view(o, k)});
+    rc = launch_xor_ops(ctx, ops, src->n);
+    if (rc != HM_OK) {
+        hm_batch_free(ctx, o);
+        return rc;
+    }
+    *out = o;
+    return HM_OK;
+}
+
+int hm_batch_concat(hm_context *ctx, const hm_batch *const *parts, size_t count, hm_batch **out) {
+    if (!ctx || !parts || !out || count == 0) return HM_ERR_INVALID_ARGUMENT;
+    std::vector<uint64_t> degb;
+    for (size_t i = 0; i < count; ++i) {
+        if (!parts[i] || parts[i]->n != parts[0]->n) return HM_ERR_INVALID_ARGUMENT;
+        degb.insert(degb.end(), parts[i]->degb.begin(), parts[i]->degb.end());
+    }
+    if (degb.size() > (size_t)hmk::MAX_SLOTS) return HM_ERR_UNSUPPORTED;
+    USE_DEV(ctx);
+    hm_batch *o = new_batch(ctx, parts[0]->n, (uint32_t)degb.size(), degb.data());
+    if (!o) return HM_ERR_INVALID_ARGUMENT;
+    int rc = alloc_batch(ctx, o);
+    if (rc != HM_OK) {
+        delete o;
+        return rc;
+    }
+    std::vector<MulOp> ops;
+    uint32_t k = 0;
+    for (size_t i = 0; i < count; ++i)
+        for (uint32_t j = 0; j < parts[i]->L; ++j, ++k) ops.push_back(MulOp{slot_view(parts[i], j), null_view(), slot_view(o, k)});
+    rc = launch_xor_ops(ctx, ops, o->n);
+    if (rc != HM_OK) {
+        hm_batch_free(ctx, o);
+        return rc;
+    }
+    *out = o;
+    return HM_OK;
+}
+
+int hm_apply2_fields(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, const uint32_t *field_bits, size_t n_fields,
+                     hm_batch **out) {
+    if (!ctx || !a || !b || !field_bits || !out || n_fields == 0) return HM_ERR_INVALID_ARGUMENT;
+    if (a->n != b->n || a->L != b->L) return HM_ERR_INVALID_ARGUMENT;
+    uint64_t total = 0;
+    for (size_t f = 0; f < n_fields; ++f) {
+        if (field_bits[f] == 0) return HM_ERR_INVALID_ARGUMENT;
+        total += field_bits[f];
+    }
+    if (total != a->L) return HM_ERR_INVALID_LENGTH;
+    int rc = validate_operation(ctx, op);
+    if (rc != HM_OK) return rc;
+    std::vector<hm_batch *> res(n_fields, nullptr);
+    uint32_t first = 0;
+    for (size_t f = 0; f < n_fields && rc == HM_OK; ++f) {
+        hm_batch *fa = nullptr, *fb = nullptr;
+        rc = hm_batch_slice(ctx, a, first, field_bits[f], &fa);
+        if (rc == HM_OK) rc = hm_batch_slice(ctx, b, first, field_bits[f], &fb);
+        if (rc == HM_OK) rc = apply2_impl(ctx, op, fa, fb, &res[f]);
+        if (fa) hm_batch_free(ctx, fa);
+        if (fb) hm_batch_free(ctx, fb);
+        first += field_bits[f];
+    }
+    if (rc == HM_OK) rc = hm_batch_concat(ctx, res.data(), n_fields, out);
+    for (hm_batch *r : res)
+        if (r) hm_batch_free(ctx, r);
+    return rc;
+}
+
 // forces the generic (view based, reference order) circuit even when the fused kernel applies; used to
 // cross-check the fused adder on the GPU.
 int hm_apply2_generic(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch **out) {

@@ -142,6 +142,17 @@ void hm_host_free(void *p);
 /* Device-resident duplicate (Ciphered::clone). */
 int hm_batch_clone(hm_context *ctx, const hm_batch *b, hm_batch **out);
 
+/* Fields of a user struct (examples/simple_struct.rs:32-58).  hm_batch_slice: slots [first_bit, first_bit + n_bits) of every
+ * value as a new batch — `Ciphered::split_at` + `Ciphered::new_from_raw` on one field (first_bit + n_bits > L ->
+ * HM_ERR_INVALID_LENGTH; the reference's split_at panics).  hm_batch_concat: the slots of `count` batches of equal n, in
+ * order — the `extend_from_slice` merge of the per-field results (more than 128 slots -> HM_ERR_UNSUPPORTED).
+ * hm_apply2_fields: the whole pattern — field f covers field_bits[f] consecutive slots (sum must be L), `op` is applied to
+ * each field of a and b as its own integer and the results are concatenated; requirement check as hm_apply2. */
+int hm_batch_slice(hm_context *ctx, const hm_batch *src, uint32_t first_bit, uint32_t n_bits, hm_batch **out);
+int hm_batch_concat(hm_context *ctx, const hm_batch *const *parts, size_t count, hm_batch **out);
+int hm_apply2_fields(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, const uint32_t *field_bits, size_t n_fields,
+                     hm_batch **out);
+
 /* ---- Encrypt / decrypt ----------------------------------------------------------------
  * Context::encrypt -> Ciphered::try_cipher -> CipheredBit::cipher for n integers at once —
  * src/context.rs:463-471, src/cipher.rs:175-191, :99-115.

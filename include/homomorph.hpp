@@ -196,7 +196,10 @@ class Context;
 
 // ---- Ciphered<T>: a batch of the reference's Ciphered<T> (src/cipher.rs:126-259) ---------------------------------
 template <class T> class Ciphered {
-    static_assert(std::is_integral<T>::value, "bincode fixint little endian is reproduced for the integer types only");
+    // integers, or packed structs of integers (bincode writes the fields in order, each fixint little endian: a struct
+    // without padding has the same bytes) — examples/simple_struct.rs:12-17
+    static_assert(std::is_integral<T>::value || (std::is_trivially_copyable<T>::value && std::has_unique_object_representations<T>::value),
+                  "bincode fixint little endian is reproduced for integers and padding-free structs of integers only");
     hm_context *ctx_ = nullptr;
     hm_batch *b_ = nullptr;
     friend class Context;
@@ -319,6 +322,29 @@ class Context {
         validate<O>();
         hm_batch *o = nullptr;
         check(hm_apply2(h_, O::code, a.raw(), b.raw(), &o));
+        return Ciphered<T>(h_, o);
+    }
+    // User structs (examples/simple_struct.rs:32-58).  slice: the bits [first_bit, first_bit + 8 sizeof(U)) of every value as
+    // a Ciphered<U> (split_at + new_from_raw on one field); concat: the extend_from_slice merge into a Ciphered<T>;
+    // apply2_fields: O on every field of a and b, field f being field_bits[f] consecutive bits.
+    template <class U, class T> Ciphered<U> slice(const Ciphered<T> &c, uint32_t first_bit) const {
+        hm_batch *o = nullptr;
+        check(hm_batch_slice(h_, c.raw(), first_bit, 8 * sizeof(U), &o));
+        return Ciphered<U>(h_, o);
+    }
+    template <class T> Ciphered<T> concat(const std::vector<const hm_batch *> &parts) const {
+        hm_batch *o = nullptr;
+        check(hm_batch_concat(h_, parts.data(), parts.size(), &o));
+        if (hm_batch_bits(o) != 8 * sizeof(T)) {
+            hm_batch_free(h_, o);
+            throw CipherError("InvalidCipheredLength");
+        }
+        return Ciphered<T>(h_, o);
+    }
+    template <class O, class T> Ciphered<T> apply2_fields(const Ciphered<T> &a, const Ciphered<T> &b, const std::vector<uint32_t> &field_bits) const {
+        validate<O>();
+        hm_batch *o = nullptr;
+        check(hm_apply2_fields(h_, O::code, a.raw(), b.raw(), field_bits.data(), field_bits.size(), &o));
         return Ciphered<T>(h_, o);
     }
     // Context::apply1 (src/context.rs:496-507): in place

@@ -124,6 +124,30 @@ static void gpu_tests() {
         auto d = ctx.decrypt(p);
         CHECK(d[0] == 42 && d[1] == 0 && d[2] == 16);
     }
+    {   // examples/simple_struct.rs — Vec3 { x, y, z: u16 } added field by field at (64,32,1,32): {1,2,3} + {4,5,6} = {5,7,9}
+        struct Vec3 {
+            uint16_t x, y, z;
+            bool operator==(const Vec3 &o) const { return x == o.x && y == o.y && z == o.z; }
+        };
+        Context ctx(Parameters(64, 32, 1, 32));
+        ctx.generate_secret_key(seeded_random(61));
+        ctx.generate_public_key(seeded_random(62));
+        std::vector<Vec3> a = {{1, 2, 3}, {65535, 1000, 7}}, b = {{4, 5, 6}, {1, 2345, 65530}};
+        auto ca = ctx.encrypt(a, masks(ctx, 2, 48, 17)), cb = ctx.encrypt(b, masks(ctx, 2, 48, 18));
+        CHECK(ca.bits() == 48);
+        auto c = ctx.apply2_fields<HomomorphicAddition>(ca, cb, {16, 16, 16});
+        auto d = ctx.decrypt(c);
+        CHECK((d[0] == Vec3{5, 7, 9}) && (d[1] == Vec3{0, 3345, 1}));
+        // the same by hand: split_at / new_from_raw / extend_from_slice
+        auto ay = ctx.slice<uint16_t>(ca, 16), by = ctx.slice<uint16_t>(cb, 16);
+        CHECK(ctx.decrypt(ay) == (std::vector<uint16_t>{2, 1000}));
+        auto x = ctx.apply2<HomomorphicAddition>(ctx.slice<uint16_t>(ca, 0), ctx.slice<uint16_t>(cb, 0));
+        auto y = ctx.apply2<HomomorphicAddition>(ay, by);
+        auto z = ctx.apply2<HomomorphicAddition>(ctx.slice<uint16_t>(ca, 32), ctx.slice<uint16_t>(cb, 32));
+        auto m = ctx.concat<Vec3>({x.raw(), y.raw(), z.raw()});
+        CHECK(m.to_host() == c.to_host());
+        CHECK(throws<CipherError>([&] { ctx.slice<uint16_t>(ca, 40); }));
+    }
     {   // context.rs:310-323 — requirement check: d/delta = 16 < 21
         Context ctx(Parameters(64, 16, 4, 16));
         ctx.generate_secret_key(seeded_random(51));

@@ -504,6 +504,51 @@ def test_mul_circuit_plans_agree(oracle, hm, force_thread):
     np.testing.assert_array_equal(ctx.decrypt(r), a * b)
 
 
+@pytest.mark.parametrize("params", [(64, 32, 1, 32), CONFIG_A])
+def test_struct_fields(oracle, hm, params):
+    """examples/simple_struct.rs: Vec3 { x, y, z: u16 } added field by field (split_at / new_from_raw / extend_from_slice,
+    :32-58; main :62-74 expects {1,2,3} + {4,5,6} = {5,7,9} at (64,32,1,32)) — hm_batch_slice / hm_batch_concat /
+    hm_apply2_fields against the oracle's adder run on every field separately."""
+    rng = np.random.default_rng(11)
+    sk, pk, ctx = setup(oracle, hm, params, 23)
+    vec3 = np.dtype([("x", "<u2"), ("y", "<u2"), ("z", "<u2")])
+    n, L = 9, 48
+    a = np.zeros(n, dtype=vec3)
+    b = np.zeros(n, dtype=vec3)
+    for f in vec3.names:
+        a[f] = rng.integers(0, 1 << 16, size=n)
+        b[f] = rng.integers(0, 1 << 16, size=n)
+    a[0], b[0] = (1, 2, 3), (4, 5, 6)
+    ma = masks_for(rng, n, L, params[3]).reshape(n, L, -1)
+    mb = masks_for(rng, n, L, params[3]).reshape(n, L, -1)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    assert ca.bits == 48
+    r = ctx.apply2_fields(hm.HomomorphicAddition, ca, cb, [16, 16, 16])
+    widths = list(r.slot_words())
+    assert len(widths) == 48
+    exp = []
+    for i, f in enumerate(vec3.names):
+        oa = oracle_encrypt(oracle, pk, np.ascontiguousarray(a[f]), np.ascontiguousarray(ma[:, 16 * i:16 * i + 16]).reshape(-1))
+        ob = oracle_encrypt(oracle, pk, np.ascontiguousarray(b[f]), np.ascontiguousarray(mb[:, 16 * i:16 * i + 16]).reshape(-1))
+        want, _ = oracle.apply(oracle.OP_ADD, oa, ob, 16, threads=oracle.max_threads())
+        exp.append(expected_padded(want, n, widths[16 * i:16 * i + 16]))
+    np.testing.assert_array_equal(r.to_host().reshape(n, -1), np.concatenate(exp, axis=1))
+    dec = ctx.decrypt(r, dtype=vec3)
+    assert tuple(dec[0]) == (5, 7, 9)
+    for f in vec3.names:
+        np.testing.assert_array_equal(dec[f], a[f] + b[f])
+    # the pieces on their own: slice + concat is the identity, a field is an integer batch, bounds are checked
+    parts = [ca.slice(0, 16, np.uint16), ca.slice(16, 32)]
+    np.testing.assert_array_equal(ctx.concat(parts).to_host(), ca.to_host())
+    np.testing.assert_array_equal(ctx.decrypt(parts[0]), a["x"])
+    y = ctx.apply2(hm.HomomorphicAddition, ca.slice(16, 16, np.uint16), cb.slice(16, 16, np.uint16))
+    np.testing.assert_array_equal(ctx.decrypt(y), a["y"] + b["y"])
+    with pytest.raises(hm.InvalidCipheredLength):
+        ca.slice(40, 16)
+    with pytest.raises(hm.InvalidCipheredLength):
+        ctx.apply2_fields(hm.HomomorphicAddition, ca, cb, [16, 16])
+
+
 def test_empty_batches(oracle, hm):
     """n = 0 everywhere (the reference's Vec-based API accepts empty inputs)."""
     sk, pk, ctx = setup(oracle, hm, CONFIG_A, 2)
