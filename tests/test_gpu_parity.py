@@ -549,6 +549,39 @@ def test_struct_fields(oracle, hm, params):
         ctx.apply2_fields(hm.HomomorphicAddition, ca, cb, [16, 16])
 
 
+def test_add_u128(oracle, hm):
+    """u128 (impl list of src/impls/numbers/uint.rs:98-105): 128 bit-ciphertexts per value, the same ripple-carry circuit;
+    slot 127 has degree bound 380 * 256.  Fused kernel and regrouped generic plan against the oracle."""
+    rng = np.random.default_rng(128)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 28)
+    u128 = np.dtype([("lo", "<u8"), ("hi", "<u8")])
+    n, L = 3, 128
+    a = np.zeros(n, dtype=u128)
+    b = np.zeros(n, dtype=u128)
+    for f in u128.names:
+        a[f] = rng.integers(0, 1 << 64, size=n, dtype=np.uint64)
+        b[f] = rng.integers(0, 1 << 64, size=n, dtype=np.uint64)
+    a[0], b[0] = (2**64 - 1, 2**64 - 1), (1, 0)  # carry through all 128 bits -> 0
+    ma, mb = masks_for(rng, n, L, 128), masks_for(rng, n, L, 128)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    assert ca.bits == 128
+    r = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+    widths = list(r.slot_words())
+    assert widths[0] == 5 and widths[127] == (380 * 256) // 64 + 1
+    raw = lambda x: np.frombuffer(x.tobytes(), dtype=np.uint8)
+    oa, _ = oracle.encrypt(pk, raw(a), 16, ma, threads=oracle.max_threads())
+    ob, _ = oracle.encrypt(pk, raw(b), 16, mb, threads=oracle.max_threads())
+    want, _ = oracle.apply(oracle.OP_ADD, oa, ob, L, threads=oracle.max_threads())
+    got = r.to_host()
+    np.testing.assert_array_equal(got, expected_padded(want, n, widths))
+    np.testing.assert_array_equal(ctx.apply2(hm.HomomorphicAddition, ca, cb, generic=True).to_host(), got)
+    dec = ctx.decrypt(r, dtype=u128)
+    for i in range(n):
+        x = (int(a["hi"][i]) << 64 | int(a["lo"][i])) + (int(b["hi"][i]) << 64 | int(b["lo"][i]))
+        assert (int(dec["hi"][i]) << 64 | int(dec["lo"][i])) == x % (1 << 128)
+    assert tuple(dec[0]) == (0, 0)
+
+
 def test_empty_batches(oracle, hm):
     """n = 0 everywhere (the reference's Vec-based API accepts empty inputs)."""
     sk, pk, ctx = setup(oracle, hm, CONFIG_A, 2)
