@@ -575,6 +575,11 @@ def test_add_u128(oracle, hm):
     got = r.to_host()
     np.testing.assert_array_equal(got, expected_padded(want, n, widths))
     np.testing.assert_array_equal(ctx.apply2(hm.HomomorphicAddition, ca, cb, generic=True).to_host(), got)
+    try:  # and the thread-per-value kernel (normally for batches of >= 256 values per SM)
+        hm.lib().hm_set_tuning(b"adder_thread_min", 0)
+        np.testing.assert_array_equal(ctx.apply2(hm.HomomorphicAddition, ca, cb).to_host(), got)
+    finally:
+        hm.lib().hm_set_tuning(b"adder_thread_min", -1)
     dec = ctx.decrypt(r, dtype=u128)
     for i in range(n):
         x = (int(a["hi"][i]) << 64 | int(a["lo"][i])) + (int(b["hi"][i]) << 64 | int(b["lo"][i]))
