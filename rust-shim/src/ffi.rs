@@ -38,6 +38,9 @@ extern "C" {
     pub fn hm_batch_value_words(b: *const hm_batch) -> usize;
     pub fn hm_batch_download(ctx: *mut hm_context, b: *const hm_batch, host: *mut u64) -> c_int;
     pub fn hm_batch_free(ctx: *mut hm_context, b: *mut hm_batch);
+    pub fn hm_batch_slice(ctx: *mut hm_context, src: *const hm_batch, first_bit: u32, n_bits: u32, out: *mut *mut hm_batch) -> c_int;
+    pub fn hm_batch_concat(ctx: *mut hm_context, parts: *const *const hm_batch, count: usize, out: *mut *mut hm_batch) -> c_int;
+    pub fn hm_apply2_fields(ctx: *mut hm_context, op: c_int, a: *const hm_batch, b: *const hm_batch, field_bits: *const u32, n_fields: usize, out: *mut *mut hm_batch) -> c_int;
     pub fn hm_host_alloc(bytes: usize) -> *mut c_void;
     pub fn hm_host_free(p: *mut c_void);
 }
