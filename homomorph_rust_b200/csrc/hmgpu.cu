@@ -24,6 +24,8 @@
 namespace hmk {
 cudaError_t launch_mulrem_fresh_b(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
                                   int sm_count, cudaStream_t stream); // kernels_b.cu
+cudaError_t launch_mulrem_fresh_b32(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
+                                    int sm_count, cudaStream_t stream); // kernels_b.cu
 }
 
 // tuning knobs (hm_set_tuning): minimum batch size for the thread-per-value adder; < 0 = default (256 values per SM)
@@ -420,7 +422,7 @@ int launch_rem(hm_context *ctx, View a, View o, size_t n) {
     const bool fold = (ds % 32 == 0) && (ds / 32 == 2 || ds / 32 == 4 || ds / 32 == 8 || ds / 32 == 16);
     if (fold) {
         const int ws = (int)(ds / 32);
-        const size_t smem = (size_t)4 * 256 * ws * 4;
+        const size_t smem = (size_t)4 * 256 * (ws >= 8 ? ws + 4 : ws) * 4; // rem_fold_row_stride
         const unsigned grid = (unsigned)((n + 127) / 128);
 #define REM_CASE(WS)                                                                                                  \
     case WS:                                                                                                          \
@@ -2166,7 +2168,9 @@ static int mulrem_fresh_exec(hm_context *ctx, const hm_batch *a, const hm_batch 
     const uint64_t pairs = (uint64_t)a->n * a->L;
     if (!pairs) return HM_OK;
     if (ctx->fresh_deg == 1024) {
-        CK(hmk::launch_mulrem_fresh_b(a->d, b->d, o->d, pairs, ctx->d_remT, ctx->sm_count, ctx->stream));
+        static const int mode_b = getenv("HM_MULREM_B_MODE") ? atoi(getenv("HM_MULREM_B_MODE")) : 1; // 0 = fully unrolled first kernel
+        if (mode_b) CK(hmk::launch_mulrem_fresh_b32(a->d, b->d, o->d, pairs, ctx->d_remT, ctx->sm_count, ctx->stream));
+        else CK(hmk::launch_mulrem_fresh_b(a->d, b->d, o->d, pairs, ctx->d_remT, ctx->sm_count, ctx->stream));
         ctx->launches++;
         return HM_OK;
     }

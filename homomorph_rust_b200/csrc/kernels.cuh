@@ -976,12 +976,14 @@ static __global__ void __launch_bounds__(128, 4) mul_warp_kernel(const MulOp *__
 // ----------------------------------------------------------------------------------------
 // REP > 1: every table row is stored REP times, copy `rep` of a row starts (rep * WS) words after copy 0, so that
 // the lanes of a quarter-warp (rep = lane % 8) read from disjoint bank groups whatever their indices are.
-template <int WS, int REP = 1>
+// RS = row stride in words (>= WS): a stride that is an odd number of 16-byte groups spreads the rows of a
+// quarter-warp over all eight bank groups (with RS = WS = 16 every row starts in group 0 or 4: 4-way conflicts).
+template <int WS, int REP = 1, int RS = WS>
 __device__ __forceinline__ void fold_word(uint32_t (&dst)[WS], uint32_t t, const uint32_t *__restrict__ T, uint32_t rep = 0) {
-    const uint32_t *r0 = T + ((size_t)(0 * 256 + (t & 255u)) * REP + rep) * WS;
-    const uint32_t *r1 = T + ((size_t)(1 * 256 + ((t >> 8) & 255u)) * REP + rep) * WS;
-    const uint32_t *r2 = T + ((size_t)(2 * 256 + ((t >> 16) & 255u)) * REP + rep) * WS;
-    const uint32_t *r3 = T + ((size_t)(3 * 256 + (t >> 24)) * REP + rep) * WS;
+    const uint32_t *r0 = T + ((size_t)(0 * 256 + (t & 255u)) * REP + rep) * RS;
+    const uint32_t *r1 = T + ((size_t)(1 * 256 + ((t >> 8) & 255u)) * REP + rep) * RS;
+    const uint32_t *r2 = T + ((size_t)(2 * 256 + ((t >> 16) & 255u)) * REP + rep) * RS;
+    const uint32_t *r3 = T + ((size_t)(3 * 256 + (t >> 24)) * REP + rep) * RS;
     if constexpr (WS % 4 == 0) {
 #pragma unroll
         for (int q = 0; q < WS / 4; ++q) {
@@ -998,10 +1000,12 @@ __device__ __forceinline__ void fold_word(uint32_t (&dst)[WS], uint32_t t, const
     }
 }
 
+template <int WS> __host__ __device__ constexpr int rem_fold_row_stride() { return WS >= 8 ? WS + 4 : WS; } // see fold_word
 template <int WS>
 __global__ void __launch_bounds__(128) rem_fold_kernel(View a, View o, uint64_t n, const uint32_t *__restrict__ Tg) {
     extern __shared__ __align__(16) uint32_t smem32[];
-    for (uint32_t i = threadIdx.x; i < 4u * 256u * WS; i += blockDim.x) smem32[i] = Tg[i];
+    constexpr int RS = rem_fold_row_stride<WS>();
+    for (uint32_t i = threadIdx.x; i < 4u * 256u * WS; i += blockDim.x) smem32[(i / WS) * RS + (i % WS)] = Tg[i];
     __syncthreads();
     const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
@@ -1015,7 +1019,7 @@ __global__ void __launch_bounds__(128) rem_fold_kernel(View a, View o, uint64_t 
 #pragma unroll
         for (int q = WS - 1; q > 0; --q) r[q] = r[q - 1];
         r[0] = p[i];
-        if (t) fold_word<WS>(r, t, smem32);
+        if (t) fold_word<WS, 1, RS>(r, t, smem32);
     }
     uint32_t *out = reinterpret_cast<uint32_t *>(o.base + v * o.stride + o.off);
 #pragma unroll
@@ -1974,6 +1978,113 @@ static __global__ void __launch_bounds__(128, 4) mul_thread32_kernel(const MulOp
         }
     }
     if (xi == 0 && xtop && ytop && nx + ny < no) atomicXor(go + nx + ny, 1u);
+}
+
+// ----------------------------------------------------------------------------------------
+// K5b  fused (a*b) mod S for fresh pairs at D = 1024 (32 words + the X^1024 coefficient), d = 32*WS — config B.
+// The fully unrolled 32-word Karatsuba of mulrem_fresh_kernel<32,...> is 243 inlined leaves (instruction-fetch bound,
+// 255 registers, spills); here the product is the rolled mul32_acc (nine 8x8-word products, one code copy) with both
+// operands in per-thread shared-memory columns ([word pair][thread], fetched by cp.async), the 2049-bit product goes back
+// to the same columns and is folded down by a rolled sliding-window loop (16-word state in registers, words read
+// top-down from shared memory, 4 x 256-entry tables).  One thread per pair, 512 threads per CTA, one CTA per SM.
+// ----------------------------------------------------------------------------------------
+template <int STRIDE>
+__device__ __forceinline__ void mul32_acc_ss(const uint2 *__restrict__ m, const uint2 *__restrict__ c, uint32_t (&t)[64]) {
+#pragma unroll 1
+    for (int i = 0; i < 9; ++i) {
+        const uint32_t sel = (uint32_t)(0xFA5C84321ull >> (4 * i)) & 0xFu; // as in mul32_acc
+        uint32_t x[8], y[8], r[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = y[q] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (sel >> b & 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint2 u = m[(4 * b + q) * STRIDE];
+                    const uint2 w = c[(4 * b + q) * STRIDE];
+                    x[2 * q] ^= u.x; x[2 * q + 1] ^= u.y;
+                    y[2 * q] ^= w.x; y[2 * q + 1] ^= w.y;
+                }
+            }
+        }
+        clmul_kara<8>(x, y, r);
+        switch (i) {
+            case 0: xor16_at64<0>(t, r); xor16_at64<8>(t, r); xor16_at64<16>(t, r); xor16_at64<24>(t, r); break;
+            case 1: xor16_at64<16>(t, r); xor16_at64<8>(t, r); xor16_at64<32>(t, r); xor16_at64<24>(t, r); break;
+            case 2: xor16_at64<8>(t, r); xor16_at64<24>(t, r); break;
+            case 3: xor16_at64<32>(t, r); xor16_at64<40>(t, r); xor16_at64<16>(t, r); xor16_at64<24>(t, r); break;
+            case 4: xor16_at64<48>(t, r); xor16_at64<40>(t, r); xor16_at64<32>(t, r); xor16_at64<24>(t, r); break;
+            case 5: xor16_at64<40>(t, r); xor16_at64<24>(t, r); break;
+            case 6: xor16_at64<16>(t, r); xor16_at64<24>(t, r); break;
+            case 7: xor16_at64<32>(t, r); xor16_at64<24>(t, r); break;
+            default: xor16_at64<24>(t, r); break;
+        }
+    }
+}
+
+constexpr int MR32_THREADS = 512;
+constexpr int MR32_PAIRS = 34; // per thread: a = pairs 0..16 (16 = the top coefficient's word), b = pairs 17..33
+template <int WS> __host__ __device__ constexpr int mulrem32_row_stride() { return WS + 4; } // words: 5 bank groups of 16 B for WS = 16
+template <int WS> constexpr size_t mulrem32_smem_bytes() { return (size_t)4 * 256 * mulrem32_row_stride<WS>() * 4 + (size_t)MR32_PAIRS * MR32_THREADS * 8; }
+
+template <int WS>
+__global__ void __launch_bounds__(MR32_THREADS, 1) mulrem_fresh32_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
+                                                                      uint64_t *__restrict__ O, uint64_t n,
+                                                                      const uint32_t *__restrict__ Tg) {
+    constexpr int WD = 32, WF = WD / 2 + 1, TH = MR32_THREADS;
+    extern __shared__ __align__(16) uint32_t smem32[];
+    constexpr int RS = mulrem32_row_stride<WS>();
+    uint32_t *T = smem32;
+    uint2 *col = reinterpret_cast<uint2 *>(smem32 + 4 * 256 * RS) + threadIdx.x; // pair q of this thread at col[q * TH]
+    for (uint32_t i = threadIdx.x; i < 4u * 256u * WS; i += TH) T[(i / WS) * RS + (i % WS)] = Tg[i];
+    __syncthreads();
+    const uint32_t scol = (uint32_t)__cvta_generic_to_shared(col);
+    for (uint64_t u = (uint64_t)blockIdx.x * TH + threadIdx.x; u < n; u += (uint64_t)gridDim.x * TH) {
+        const uint64_t *ga = A + u * WF, *gb = B + u * WF;
+#pragma unroll
+        for (int q = 0; q < WF; ++q) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(scol + q * TH * 8), "l"(ga + q) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(scol + (WF + q) * TH * 8), "l"(gb + q) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        uint32_t t[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) t[i] = 0;
+        mul32_acc_ss<TH>(col, col + WF * TH, t);
+        // the X^1024 coefficients: (a' + at X^1024)(b' + bt X^1024) = a'b' + X^1024 (at b' + bt a') + at bt X^2048
+        const uint32_t atop = col[16 * TH].x & 1u, btop = col[(WF + 16) * TH].x & 1u;
+        const uint32_t ma = 0u - atop, mb = 0u - btop;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const uint2 x = col[q * TH], y = col[(WF + q) * TH];
+            t[32 + 2 * q] ^= (y.x & ma) ^ (x.x & mb);
+            t[32 + 2 * q + 1] ^= (y.y & ma) ^ (x.y & mb);
+        }
+        // product words 0..63 back into the columns (the operands are dead now); word 64 = at & bt stays in a register
+#pragma unroll
+        for (int q = 0; q < 32; ++q) col[q * TH] = make_uint2(t[2 * q], t[2 * q + 1]);
+        const uint32_t *pw = reinterpret_cast<const uint32_t *>(col); // word i at pw[(i / 2) * TH * 2 + (i & 1)]
+        // sliding-window fold: r = product words [i - WS, i), top = word i, for i = 64 down to WS
+        uint32_t r[WS];
+#pragma unroll
+        for (int q = 0; q < WS; ++q) r[q] = t[64 - WS + q];
+        uint32_t top = atop & btop;
+        if (top) fold_word<WS, 1, RS>(r, top, T);
+#pragma unroll 16
+        for (int i = 63; i >= WS; --i) {
+            top = r[WS - 1];
+#pragma unroll
+            for (int q = WS - 1; q > 0; --q) r[q] = r[q - 1];
+            const int w = i - WS;
+            r[0] = pw[(w >> 1) * TH * 2 + (w & 1)];
+            if (top) fold_word<WS, 1, RS>(r, top, T);
+        }
+        uint32_t *out = reinterpret_cast<uint32_t *>(O + u * (WS / 2));
+#pragma unroll
+        for (int q = 0; q < WS / 4; ++q) reinterpret_cast<uint4 *>(out)[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    }
 }
 
 // ----------------------------------------------------------------------------------------
