@@ -1037,7 +1037,7 @@ static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint
     int path = 0; // 0 generic, 1 config A tables, 2 config B tables
     if (ctx->enc_table_in_smem && masks_aligned && p.wf == 5 && ctx->tau == 128 && p.wb == 8) path = 1;
     if (ctx->enc_table_in_smem && masks_aligned && p.wf == 17 && ctx->tau == 256 && p.wb == 4 &&
-        table_bytes + 2 * (size_t)hmk::ENC_THREADS * 17 * 8 <= ctx->smem_optin)
+        table_bytes + 2 * (size_t)256 * 17 * 8 <= ctx->smem_optin) // 256-thread CTAs: table 136 KB + 2 x 34 KB of staging
         path = 2;
     static const int enc_mode = getenv("HM_ENC_MODE") ? atoi(getenv("HM_ENC_MODE")) : 1;
     if (path == 1 && enc_mode == 1 && ctx->d_enc_table6) {
@@ -1054,12 +1054,12 @@ static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint
         kern<<<grid, hmk::ENC_THREADS, smem, ctx->stream>>>(p);
         LAUNCHED("encrypt_tab_kernel<5,4,8>");
     } else if (path == 2) {
-        const size_t smem = table_bytes + 2 * (size_t)hmk::ENC_THREADS * 17 * 8;
-        auto kern = hmk::encrypt_tab_kernel<17, 8, 4>;
+        const size_t smem = table_bytes + 2 * (size_t)256 * 17 * 8;
+        auto kern = hmk::encrypt_tab_kernel<17, 8, 4, 256>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int grid = grid_for(ctx, p.units, hmk::ENC_THREADS, 1);
-        kern<<<grid, hmk::ENC_THREADS, smem, ctx->stream>>>(p);
-        LAUNCHED("encrypt_tab_kernel<17,8,4>");
+        const int grid = grid_for(ctx, p.units, 256, 1);
+        kern<<<grid, 256, smem, ctx->stream>>>(p);
+        LAUNCHED("encrypt_tab_kernel<17,8,4,256>");
     } else {
         const size_t smem = ctx->enc_table_in_smem ? (size_t)p.table_words * 8 : 0;
         CK(cudaFuncSetAttribute(hmk::encrypt_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

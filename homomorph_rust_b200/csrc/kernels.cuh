@@ -168,30 +168,30 @@ struct EncParams {
 constexpr int ENC_THREADS = 512;
 
 // Fast path: WF words per slot, MW 32-bit mask words (tau == 32*MW), window WB.
-template <int WF, int MW, int WB>
-__global__ void __launch_bounds__(ENC_THREADS, 1) encrypt_tab_kernel(EncParams p) {
+template <int WF, int MW, int WB, int TH = ENC_THREADS>
+__global__ void __launch_bounds__(TH, 1) encrypt_tab_kernel(EncParams p) {
     extern __shared__ __align__(16) uint64_t smem64[];
     uint64_t *tab = smem64;                              // table_words
-    uint64_t *stage = smem64 + ((p.table_words + 1) & ~1u); // 2 x ENC_THREADS*WF, 16-byte aligned
+    uint64_t *stage = smem64 + ((p.table_words + 1) & ~1u); // 2 x TH*WF, 16-byte aligned
     const int tid = threadIdx.x;
     // table: global -> shared, 128-bit coalesced
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.table);
         uint4 *dst = reinterpret_cast<uint4 *>(tab);
         const uint32_t n16 = p.table_words / 2;
-        for (uint32_t i = tid; i < n16; i += ENC_THREADS) dst[i] = __ldg(src + i);
+        for (uint32_t i = tid; i < n16; i += TH) dst[i] = __ldg(src + i);
         if ((p.table_words & 1) && tid == 0) tab[p.table_words - 1] = p.table[p.table_words - 1];
     }
     __syncthreads();
     constexpr int GROUPS = MW * 32 / WB;
-    const uint64_t ntiles = (p.units + ENC_THREADS - 1) / ENC_THREADS;
+    const uint64_t ntiles = (p.units + TH - 1) / TH;
     uint32_t it = 0;
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        uint64_t *st = stage + (size_t)(it & 1) * ENC_THREADS * WF;
+        uint64_t *st = stage + (size_t)(it & 1) * TH * WF;
         // the bulk store issued two iterations ago from this buffer must have read it
         if (tid == 0) tma_store_wait_read<1>();
         __syncthreads();
-        const uint64_t u = t * ENC_THREADS + tid;
+        const uint64_t u = t * TH + tid;
         uint64_t acc[WF];
 #pragma unroll
         for (int j = 0; j < WF; ++j) acc[j] = 0;
@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encrypt_tab_kernel(EncParams p
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
-            const uint64_t first = t * ENC_THREADS;
-            const uint64_t cnt = (p.units - first < ENC_THREADS) ? (p.units - first) : ENC_THREADS;
+            const uint64_t first = t * TH;
+            const uint64_t cnt = (p.units - first < TH) ? (p.units - first) : TH;
             const uint32_t bytes = (uint32_t)(cnt * WF * 8);
             if ((bytes & 15u) == 0) {
                 tma_store_1d(p.out + first * WF, st, bytes);
