@@ -28,7 +28,7 @@ cudaError_t launch_mulrem_fresh_b32(const uint64_t *A, const uint64_t *B, uint64
                                     int sm_count, cudaStream_t stream); // kernels_b.cu
 }
 
-// tuning knobs (hm_set_tuning): minimum batch size for the thread-per-value adder; < 0 = default (256 values per SM)
+// tuning knobs (hm_set_tuning): minimum batch size for the thread-per-value adder; < 0 = default (96 values per SM)
 static long g_adder_thread_min = -1;
 static long g_mul_thread_min = -1; // minimum (values x chunks) for the thread-per-chunk multiply; < 0 = default (128 per SM)
 static long g_mul_thread_chunk = 32; // 24 = the first thread-per-chunk kernel (3-way Karatsuba chunks)
@@ -1847,7 +1847,7 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                 static const int mode = getenv("HM_ADDER_MODE") ? atoi(getenv("HM_ADDER_MODE")) : 5;
                 // the thread-per-value kernel needs tens of thousands of values to fill the GPU (one value per thread);
                 // smaller batches (and the chunks of the host pipeline) use the warp-per-value kernel
-                if (mode >= 3 && wd == 8 && n >= (g_adder_thread_min >= 0 ? (size_t)g_adder_thread_min : (size_t)ctx->sm_count * 256)) { // thread-per-value Karatsuba chain; mode - 1 = CTAs per SM
+                if (mode >= 3 && wd == 8 && n >= (g_adder_thread_min >= 0 ? (size_t)g_adder_thread_min : (size_t)ctx->sm_count * 96)) { // thread-per-value Karatsuba chain; mode - 1 = CTAs per SM (cross-over measured: tools/adder_crossover.py)
                     const int per_sm = mode - 1;
                     const int blocks = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->sm_count * per_sm);
                     static const int use_smem = getenv("HM_ADDER_SMEM") ? atoi(getenv("HM_ADDER_SMEM")) : 1; // 0 = first thread kernel (scratch in global memory)
