@@ -1848,7 +1848,7 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                 // the thread-per-value kernel needs tens of thousands of values to fill the GPU (one value per thread);
                 // smaller batches (and the chunks of the host pipeline) use the warp-per-value kernel
                 if (mode >= 3 && wd == 8 && n >= (g_adder_thread_min >= 0 ? (size_t)g_adder_thread_min : (size_t)ctx->sm_count * 96)) { // thread-per-value Karatsuba chain; mode - 1 = CTAs per SM (cross-over measured: tools/adder_crossover.py)
-                    const int per_sm = mode - 1;
+                    const int per_sm = (mode - 1 == 3) ? 3 : 4; // 128-thread CTAs per SM (168 or 128 registers per thread)
                     const int blocks = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->sm_count * per_sm);
                     static const int use_smem = getenv("HM_ADDER_SMEM") ? atoi(getenv("HM_ADDER_SMEM")) : 1; // 0 = first thread kernel (scratch in global memory)
                     if (use_smem && (per_sm == 3 || per_sm == 4)) { // working set in shared memory, chunks prefetched by cp.async
@@ -1861,7 +1861,7 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                     }
                     uint32_t *scratch = nullptr;
                     CK(cudaMallocAsync(&scratch, (size_t)blocks * 128 * hmk::ADT_THREAD_WORDS * 4, ctx->stream));
-                    auto tk = per_sm == 2 ? hmk::adder_thread_kernel<2> : (per_sm == 3 ? hmk::adder_thread_kernel<3> : (per_sm == 4 ? hmk::adder_thread_kernel<4> : (per_sm == 5 ? hmk::adder_thread_kernel<5> : (per_sm == 6 ? hmk::adder_thread_kernel<6> : hmk::adder_thread_kernel<8>))));
+                    auto tk = hmk::adder_thread_kernel<4>; // the first thread kernel (scratch in global memory), HM_ADDER_SMEM=0
                     tk<<<blocks, 128, 0, ctx->stream>>>(a->d, b->d, o->d, n, a->L, make_layout(o), scratch);
                     rc = post_launch(ctx, "adder_thread_kernel");
                     cudaFreeAsync(scratch, ctx->stream);

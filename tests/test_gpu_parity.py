@@ -214,7 +214,7 @@ def test_poly_mul_rem(oracle, hm, wa, wb):
     np.testing.assert_array_equal(s.to_host(), expected_padded(wants, n, s.slot_words()))
 
 
-@pytest.mark.parametrize("params,n", [(CONFIG_A, 1000), (CONFIG_A, 128 * 7), (CONFIG_B, 200), ((64, 32, 8, 32), 77), ((6, 3, 2, 5), 30)])
+@pytest.mark.parametrize("params,n", [(CONFIG_A, 1000), (CONFIG_A, 128 * 7), (CONFIG_B, 200), (CONFIG_B, 512 * 3 + 40), ((64, 32, 8, 32), 77), ((6, 3, 2, 5), 30)])
 def test_mulrem_fresh(oracle, hm, params, n):
     """The BASELINE `mul+rem` unit on pairs of fresh ciphertexts (fused kernel at config A)."""
     rng = np.random.default_rng(n)
