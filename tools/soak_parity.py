@@ -82,5 +82,26 @@ for op, oop, nm in ((hm.HomomorphicAndGate, orc.OP_AND, "AND"), (hm.HomomorphicO
     wg, _ = orc.apply(oop, oa, ob, 32, threads=T)
     check(f"{nm} gate on fresh u32 batches", g.to_host(), expected_padded(wg, n, g.slot_words()), t0)
 
+# config B (d = d' = 512, tau = 256, delta = 8): table encrypt, fused mul+rem, regrouped generic adder
+del ctx
+B = (512, 512, 8, 256)
+sk, pk, skb, pkb = keys(orc, *B, 778)
+ctx = engine_context(hm, *B, skb, pkb)
+t0 = time.time(); n = 20_000
+a = rng.integers(0, 256, size=n, dtype=np.uint8); b = rng.integers(0, 256, size=n, dtype=np.uint8)
+ma, mb = rb(11, n * 8 * 32), rb(12, n * 8 * 32)
+ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+oa, ob = oracle_encrypt(orc, pk, a, ma), oracle_encrypt(orc, pk, b, mb)
+check("config B: encrypt u8 (4-bit-window table kernel)", ca.to_host(), expected_padded(oa, n, [17] * 8), t0)
+check("config B: decrypt fresh u8", ctx.decrypt(ca), orc.decrypt(sk, oa, 8, threads=T)[0], t0)
+r = ctx.poly_mulrem(ca, cb)
+wr, _ = orc.poly_mulrem(oa, ob, sk, threads=T)
+check("config B: mul+rem on fresh pairs (160 k pairs)", r.to_host(), expected_padded(wr, n, [8] * 8), t0)
+t0 = time.time(); n = 600
+s = ctx.apply2(hm.HomomorphicAddition, ctx.encrypt(a[:n], ma[: n * 256]), ctx.encrypt(b[:n], mb[: n * 256]))
+ws, _ = orc.apply(orc.OP_ADD, oracle_encrypt(orc, pk, a[:n], ma[: n * 256]), oracle_encrypt(orc, pk, b[:n], mb[: n * 256]), 8, threads=T)
+check("config B: u8 add (regrouped generic plan)", s.to_host(), expected_padded(ws, n, s.slot_words()), t0)
+check("  decrypt after add", ctx.decrypt(s), orc.decrypt(sk, ws, 8, threads=T)[0], t0)
+
 print("ALL OK" if ok else "MISMATCH")
 sys.exit(0 if ok else 1)
