@@ -348,8 +348,15 @@ def run_ours(args, rank, local_rank, world):
             rc = lib.hm_encrypt_device_into(ctx._h, dv.data_ptr(), n, L, dm.data_ptr(), ce._h)
             assert rc == 0, rc
         s = timed(encd, reps=20)
-        extra["encrypt"] = {"value": n / s, "unit": "u32/s", "kernel": "encrypt_tab6_kernel", "ms": s * 1e3,
-                            "hbm_GBps": n * 1792 / s / 1e9, "hbm_frac": n * 1792 / s / 1e9 / hbm_peak}
+        # shared-memory side of the same kernel: 15 rotated + 1 plain warp-wide LDS.64 per 6 bit-ciphertexts, 2 wavefronts
+        # (128 B each) per LDS.64 -> 32 / 6 shared-memory cycles per bit-ciphertext per SM at best
+        props = torch.cuda.get_device_properties(local_rank)
+        sm_count, sm_clk = props.multi_processor_count, getattr(props, "clock_rate", 1965000) * 1e3  # max SM clock; the run's clocks are in "clocks"
+        extra["encrypt"] = {"value": n / s, "unit": "u32/s", "kernel": "encrypt_tab6b_kernel", "ms": s * 1e3,
+                            "hbm_GBps": n * 1792 / s / 1e9, "hbm_frac": n * 1792 / s / 1e9 / hbm_peak,
+                            "smem_frac": (n * L / s) * (32.0 / 6.0) / (sm_count * sm_clk),
+                            "note": "table lookups: 640 B of shared-memory reads per 56 B of HBM traffic, so the binding roofline is the "
+                                    "shared-memory pipe (smem_frac = LDS wavefront cycles needed / available), not HBM"}
         ce.free()
         # end-to-end encryption, host plaintexts in -> ciphertexts resident in HBM: (i) host-generated masks cross PCIe
         # (16 B per bit), (ii) masks generated on the device from a seed (Philox4x32-10), only 4 B per u32 cross

@@ -752,6 +752,11 @@ int hm_set_public_key(hm_context *ctx, const uint8_t *const *polys, const size_t
             for (uint32_t e = 0; e < 256; ++e)
                 for (uint32_t j = 0; j < 5; ++j)
                     t6[((size_t)(g / 3) * 256 + e) * 16 + 5 * (g % 3) + j] = tab[((size_t)(g << 8) + e) * 5 + j];
+        // the last line set has one real group (15): repeat its rows in the two spare classes, so that encrypt_tab6b_kernel
+        // can fetch it with one rotation-free lookup (index 0 of the spare classes stays the zero row: e = 0 is the empty subset)
+        for (uint32_t e = 0; e < 256; ++e)
+            for (uint32_t cls = 1; cls < 3; ++cls)
+                for (uint32_t j = 0; j < 5; ++j) t6[((size_t)5 * 256 + e) * 16 + 5 * cls + j] = tab[((size_t)(15u << 8) + e) * 5 + j];
         CK(cudaMalloc(&ctx->d_enc_table6, t6.size() * 8));
         CK(cudaMemcpyAsync(ctx->d_enc_table6, t6.data(), t6.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1044,7 +1049,13 @@ static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint
         const size_t smem = (size_t)hmk::ENC6_SLOTS * 256 * 128;
         CK(cudaFuncSetAttribute(hmk::encrypt_tab6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = grid_for(ctx, (p.units + 5) / 6 * 32, hmk::ENC6_THREADS, 1);
-        hmk::encrypt_tab6_kernel<<<grid, hmk::ENC6_THREADS, smem, ctx->stream>>>(p, ctx->d_enc_table6);
+        static const int enc6b = getenv("HM_ENC6B") ? atoi(getenv("HM_ENC6B")) : 1; // 0 = first version (compiler-generated index arithmetic)
+        if (enc6b) {
+            CK(cudaFuncSetAttribute(hmk::encrypt_tab6b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hmk::encrypt_tab6b_kernel<<<grid, hmk::ENC6_THREADS, smem, ctx->stream>>>(p, ctx->d_enc_table6);
+        } else {
+            hmk::encrypt_tab6_kernel<<<grid, hmk::ENC6_THREADS, smem, ctx->stream>>>(p, ctx->d_enc_table6);
+        }
         LAUNCHED("encrypt_tab6_kernel");
     } else if (path == 1) {
         const size_t smem = table_bytes + 2 * (size_t)hmk::ENC_THREADS * 5 * 8;
