@@ -1050,7 +1050,7 @@ static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint
         CK(cudaFuncSetAttribute(hmk::encrypt_tab6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = grid_for(ctx, (p.units + 5) / 6 * 32, hmk::ENC6_THREADS, 1);
         static const int enc6b = getenv("HM_ENC6B") ? atoi(getenv("HM_ENC6B")) : 1; // 0 = first version (compiler-generated index arithmetic)
-        if (enc6b) {
+        if (enc6b && p.units < ((uint64_t)1 << 31) - 6 * (uint64_t)grid * (hmk::ENC6_THREADS / 32)) {
             CK(cudaFuncSetAttribute(hmk::encrypt_tab6b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             hmk::encrypt_tab6b_kernel<<<grid, hmk::ENC6_THREADS, smem, ctx->stream>>>(p, ctx->d_enc_table6);
         } else {

@@ -343,30 +343,32 @@ static __global__ void __launch_bounds__(ENC6_THREADS, 1) encrypt_tab6b_kernel(E
         base[k] = sbase + (5 * cls + j) * 8; // rows of class cls live at words [5 cls, 5 cls + 5) of every 128-byte line
         sel[k] = 0x4440u | cls;              // PRMT: that byte -> byte 0, zeros (second source) above
     }
-    const uint64_t ngroups = (p.units + 5) / 6;
-    const uint64_t wstride = (uint64_t)gridDim.x * (ENC6_THREADS / 32);
-    uint64_t g6 = (uint64_t)blockIdx.x * (ENC6_THREADS / 32) + warp;
+    // 32-bit loop arithmetic (the host takes this kernel only for units < 2^31)
+    const uint32_t units = (uint32_t)p.units;
+    const uint32_t ngroups = (units + 5u) / 6u;
+    const uint32_t wstride = gridDim.x * (ENC6_THREADS / 32);
+    uint32_t g6 = blockIdx.x * (ENC6_THREADS / 32) + warp;
     uint4 m_nxt = make_uint4(0, 0, 0, 0);
     uint32_t b_nxt = 0;
     if (g6 < ngroups) {
-        const uint64_t u = g6 * 6 + c;
-        if (active && u < p.units) {
+        const uint32_t u = g6 * 6 + c;
+        if (active && u < units) {
             m_nxt = __ldg(reinterpret_cast<const uint4 *>(p.masks) + u);
             b_nxt = __ldg(p.values + (u >> 3));
         }
     }
     for (; g6 < ngroups; g6 += wstride) {
-        const uint64_t u = g6 * 6 + c;
+        const uint32_t u = g6 * 6 + c;
         const uint4 m4 = m_nxt;
         const uint32_t pb = b_nxt;
         {
-            const uint64_t un = (g6 + wstride) * 6 + c;
-            if (g6 + wstride < ngroups && active && un < p.units) {
+            const uint32_t un = u + wstride * 6;
+            if (active && un < units) { // un < units implies g6 + wstride < ngroups
                 m_nxt = __ldg(reinterpret_cast<const uint4 *>(p.masks) + un);
                 b_nxt = __ldg(p.values + (un >> 3));
             }
         }
-        if (!active || u >= p.units) continue;
+        if (!active || u >= units) continue;
         const uint32_t mk[5] = {m4.x, m4.y, m4.z, m4.w, 0u};
         uint32_t lo = 0, hi = 0;
         enc6_slot<0>(mk, base, sel, lo, hi);
@@ -381,7 +383,7 @@ static __global__ void __launch_bounds__(ENC6_THREADS, 1) encrypt_tab6b_kernel(E
             hi ^= xh;
         }
         if (j == 0) lo ^= (pb >> (u & 7)) & 1u;
-        *reinterpret_cast<uint2 *>(p.out + u * 5 + j) = make_uint2(lo, hi);
+        *reinterpret_cast<uint2 *>(p.out + (uint64_t)u * 5 + j) = make_uint2(lo, hi);
     }
 }
 
