@@ -79,9 +79,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_from=None, t_to=None):
+        """Summarises the samples taken inside [t_from, t_to] (the timed region); the process itself is started before the
+        warm-up steps so that nvidia-smi's start-up (NVML initialisation touches every GPU of the box) is not in the region."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -92,7 +94,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if t_from is None or (t_from <= ts <= t_to + 0.15)] or [r for (_, r) in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for nme, val in zip(names, r[4:8]):
@@ -226,12 +229,14 @@ def run_ours(args, rank, local_rank, world):
         if rc != 0:
             raise RuntimeError(f"hm_apply2_into failed: {rc} {lib.hm_last_error(ctx._h).decode()}")
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    ctx.synchronize()
+    barrier()
+    t_region0 = time.time()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     l_before = ctx.kernel_launches()
     ev[0].record(stream)
@@ -240,7 +245,7 @@ def run_ours(args, rank, local_rank, world):
         ev[i + 1].record(stream)
     ctx.synchronize()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.time()) if rank == 0 else None
     l_after = ctx.kernel_launches()
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
