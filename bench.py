@@ -567,7 +567,7 @@ def run_ours(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 words of GF(2)[X] (bit-packed, LOP3/SHF integer logic)",
+            "dtype": "u32 words of GF(2)[X] (bit-packed; carry-less products on IMAD.WIDE + LOP3)",
             "data": "synthetic (seeded keys, uniform u32 plaintexts, host-generated subset masks)",
             "config": {"workload": "configs[2]: u32 homomorphic add (ripple-carry XOR/AND circuit) on 2^18 encrypted pairs per GPU, "
                                    "d=dp=128, delta=1, tau=128", "pairs_per_gpu": n, "bits": L,
