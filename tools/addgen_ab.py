@@ -6,7 +6,7 @@ import homomorph_rust_b200 as hm
 ctx = hm.Context(hm.Parameters(512, 512, 8, 256))
 rng = np.random.default_rng(1)
 sk = hm.SecretKey.random(512, rng); ctx.set_secret_key(sk); ctx.set_public_key(hm.PublicKey.random(512, 8, 256, sk, rng))
-for n in (256, 4096):
+for n in (256, 4096, 16384):
     a = rng.integers(0, 2**32, size=n, dtype=np.uint32); b = rng.integers(0, 2**32, size=n, dtype=np.uint32)
     ca, cb = ctx.encrypt(a, seed=1), ctx.encrypt(b, seed=2)
     for mode in (0, 1):
