@@ -53,6 +53,22 @@ def test_no_cpu_fallback():
         hm.Context(hm.Parameters(128, 128, 1, 128))
 
 
+def test_null_handles_are_rejected_without_a_gpu():
+    """Every entry point checks its handles before touching CUDA: NULL context / batch -> HM_ERR_INVALID_ARGUMENT."""
+    lib = hm.lib()
+    out = C.c_void_p()
+    bad = N.HM_ERR_INVALID_ARGUMENT
+    assert lib.hm_batch_slice(None, None, 0, 8, C.byref(out)) == bad
+    assert lib.hm_batch_concat(None, None, 0, C.byref(out)) == bad
+    assert lib.hm_apply2_fields(None, N.HM_OP_ADD, None, None, None, 0, C.byref(out)) == bad
+    assert lib.hm_apply2(None, N.HM_OP_ADD, None, None, C.byref(out)) == bad
+    assert lib.hm_apply1(None, N.HM_OP_NOT, None) == bad
+    assert lib.hm_decrypt(None, None, None) == bad
+    assert lib.hm_set_tuning(b"no_such_knob", 1) == bad
+    assert lib.hm_set_tuning(b"mul_thread_chunk", 17) == bad  # 24 or 32 only
+    assert lib.hm_set_tuning(b"mul_thread_chunk", 32) == N.HM_OK
+
+
 def test_poly_degree_helper():
     lib = hm.lib()
     u64p = C.POINTER(C.c_uint64)
