@@ -25,7 +25,7 @@ namespace hmk {
 cudaError_t launch_mulrem_fresh_b(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
                                   int sm_count, cudaStream_t stream); // kernels_b.cu
 cudaError_t launch_mulrem_fresh_b32(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
-                                    int sm_count, cudaStream_t stream); // kernels_b.cu
+                                    int sm_count, cudaStream_t stream, bool reduce_first); // kernels_b.cu
 }
 
 // tuning knobs (hm_set_tuning): minimum batch size for the thread-per-value adder; < 0 = default (96 values per SM)
@@ -2179,14 +2179,15 @@ static int mulrem_fresh_exec(hm_context *ctx, const hm_batch *a, const hm_batch 
     const uint64_t pairs = (uint64_t)a->n * a->L;
     if (!pairs) return HM_OK;
     if (ctx->fresh_deg == 1024) {
-        static const int mode_b = getenv("HM_MULREM_B_MODE") ? atoi(getenv("HM_MULREM_B_MODE")) : 1; // 0 = fully unrolled first kernel
-        if (mode_b) CK(hmk::launch_mulrem_fresh_b32(a->d, b->d, o->d, pairs, ctx->d_remT, ctx->sm_count, ctx->stream));
+        // 0 = fully unrolled first kernel, 1 = rolled 32-word product then fold, 2 = operands reduced first (16-word product)
+        static const int mode_b = getenv("HM_MULREM_B_MODE") ? atoi(getenv("HM_MULREM_B_MODE")) : 2;
+        if (mode_b) CK(hmk::launch_mulrem_fresh_b32(a->d, b->d, o->d, pairs, ctx->d_remT, ctx->sm_count, ctx->stream, mode_b == 2));
         else CK(hmk::launch_mulrem_fresh_b(a->d, b->d, o->d, pairs, ctx->d_remT, ctx->sm_count, ctx->stream));
         ctx->launches++;
         return HM_OK;
     }
     constexpr int WD = 8, WS = 4;
-    static const int mode = getenv("HM_MULREM_MODE") ? atoi(getenv("HM_MULREM_MODE")) : 2;
+    static const int mode = getenv("HM_MULREM_MODE") ? atoi(getenv("HM_MULREM_MODE")) : 4;
     if (mode == 0) { // shift/mask schoolbook on the ALU pipe
         constexpr int TH = 128;
         const size_t smem = (size_t)4 * 256 * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;
@@ -2199,6 +2200,22 @@ static int mulrem_fresh_exec(hm_context *ctx, const hm_batch *a, const hm_batch 
         auto kern = hmk::mulrem_fresh_kernel<WD, WS, 2, TH, 1>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid_for(ctx, pairs, TH, 4), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
+    } else if (mode == 4 || mode == 5) { // reduce-first with the rotated conflict-free fold table (32 KB): 1024- or 512-thread CTAs
+        const int TH = mode == 4 ? 1024 : 512;
+        const size_t smem = (size_t)256 * 4 * 2 * 4 * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;
+        if (mode == 4) {
+            CK(cudaFuncSetAttribute(hmk::mulrem_fresh_a_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hmk::mulrem_fresh_a_kernel<1024><<<grid_for(ctx, pairs, TH, 1), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
+        } else {
+            CK(cudaFuncSetAttribute(hmk::mulrem_fresh_a_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hmk::mulrem_fresh_a_kernel<512><<<grid_for(ctx, pairs, TH, 1), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
+        }
+    } else if (mode == 3) { // operands reduced mod S first, then a WS-word product (same remainder, a third of the leaf products)
+        constexpr int TH = 512, REP = 8;
+        const size_t smem = (size_t)4 * 256 * REP * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;
+        auto kern = hmk::mulrem_fresh_kernel<WD, WS, 3, TH, REP>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid_for(ctx, pairs, TH, 1), TH, smem, ctx->stream>>>(a->d, b->d, o->d, pairs, ctx->d_remT);
     } else { // Karatsuba on the multiplier, one 512-thread CTA per SM, 8-way replicated (conflict-free) fold tables
         constexpr int TH = 512, REP = 8;
         const size_t smem = (size_t)4 * 256 * REP * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;

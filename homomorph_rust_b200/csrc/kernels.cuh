@@ -1216,6 +1216,64 @@ __global__ void __launch_bounds__(MR_THREADS, MINB) mulrem_fresh_kernel(const ui
                 btop = (uint32_t)gb[WD / 2] & 1u;
             }
         }
+        if constexpr (MODE == 3) {
+            // (a b) mod S = ((a mod S)(b mod S)) mod S: the remainder is unique, so reducing the operands first gives the
+            // reference's rem(mul(a, b)) bit for bit with a WS-word product (9 leaf products at WS = 4) instead of a
+            // WD-word one (27).  Fold order: word i into words [i - WS, i), top down.
+            uint32_t xa[WD + 1], xb[WD + 1];
+#pragma unroll
+            for (int j = 0; j < WD; ++j) {
+                xa[j] = a[j];
+                xb[j] = b[j];
+            }
+            xa[WD] = atop;
+            xb[WD] = btop;
+#pragma unroll
+            for (int i = WD; i >= WS; --i) {
+                uint32_t da[WS], db[WS];
+#pragma unroll
+                for (int q = 0; q < WS; ++q) {
+                    da[q] = xa[i - WS + q];
+                    db[q] = xb[i - WS + q];
+                }
+                fold_word<WS, REP>(da, xa[i], T, rep);
+                fold_word<WS, REP>(db, xb[i], T, rep);
+#pragma unroll
+                for (int q = 0; q < WS; ++q) {
+                    xa[i - WS + q] = da[q];
+                    xb[i - WS + q] = db[q];
+                }
+            }
+            uint32_t ra[WS], rb[WS], pq[2 * WS];
+#pragma unroll
+            for (int q = 0; q < WS; ++q) {
+                ra[q] = xa[q];
+                rb[q] = xb[q];
+            }
+            clmul_kara<WS>(ra, rb, pq); // degree <= 2 (32 WS - 1): 2 WS words
+#pragma unroll
+            for (int i = 2 * WS - 1; i >= WS; --i) {
+                uint32_t dst[WS];
+#pragma unroll
+                for (int q = 0; q < WS; ++q) dst[q] = pq[i - WS + q];
+                fold_word<WS, REP>(dst, pq[i], T, rep);
+#pragma unroll
+                for (int q = 0; q < WS; ++q) pq[i - WS + q] = dst[q];
+            }
+            if (u < n) {
+                uint32_t *out = reinterpret_cast<uint32_t *>(O + u * (WS / 2));
+                if constexpr (WS % 4 == 0) {
+#pragma unroll
+                    for (int q = 0; q < WS / 4; ++q)
+                        reinterpret_cast<uint4 *>(out)[q] = make_uint4(pq[4 * q], pq[4 * q + 1], pq[4 * q + 2], pq[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < WS; ++q) out[q] = pq[q];
+                }
+            }
+            __syncthreads(); // everyone is done with tiles[buf] before it is refilled
+            continue;
+        }
         uint32_t lowp[2 * WD];
         if constexpr (MODE == 0) clmul_regs<WD, WD>(a, b, lowp);
         else if constexpr (MODE == 1) clmul_imad<WD, WD>(a, b, lowp);
@@ -1248,6 +1306,148 @@ __global__ void __launch_bounds__(MR_THREADS, MINB) mulrem_fresh_kernel(const ui
                 for (int q = 0; q < WS; ++q) out[q] = pr[q];
             }
         }
+        __syncthreads(); // everyone is done with tiles[buf] before it is refilled
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// K5c  config A (D = 256, d = 128) fused mul+rem, operands reduced first (MODE 3 above) with a conflict-free fold table
+// that needs no 8-way replication: a fold is four lookups (one per byte k of the folded word) whose order is free, so
+// lane l does them in the order k = (q + l) % 4 and the 16-byte row of (table k, copy c, byte e) sits at
+// ((e * 4 + k) * 2 + c) * 16 bytes, i.e. in bank group 2 k + c whatever e is.  With c = (l >> 2) & 1 the eight lanes of a
+// quarter-warp read eight different bank groups in every LDS.128.  32 KB of tables instead of 128 KB, which leaves room
+// for 1024-thread CTAs (32 warps per SM) with double-buffered TMA tiles.
+// ----------------------------------------------------------------------------------------
+struct FoldRot {
+    uint32_t sel[4]; // PRMT selectors: byte (q + l) % 4 of the folded word -> byte 0
+    uint32_t off[4]; // shared-memory byte address of row (e = 0, k = (q + l) % 4, c)
+};
+__device__ __forceinline__ FoldRot fold_rot_init(const uint32_t *T2, int lane) {
+    FoldRot f;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(T2), c = (lane >> 2) & 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t k = (q + lane) & 3;
+        f.sel[q] = 0x4440u | k;
+        f.off[q] = sbase + (k * 2 + c) * 16;
+    }
+    return f;
+}
+__device__ __forceinline__ void fold_word_rot(uint32_t (&dst)[4], uint32_t t, const FoldRot &f) {
+    uint32_t x[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t e;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(e) : "r"(t), "r"(0u), "r"(f.sel[q]));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[q][0]), "=r"(x[q][1]), "=r"(x[q][2]), "=r"(x[q][3]) : "r"(e * 128u + f.off[q]));
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) dst[w] ^= x[0][w] ^ x[1][w] ^ x[2][w] ^ x[3][w];
+}
+
+template <int MR_THREADS>
+__global__ void __launch_bounds__(MR_THREADS, 1) mulrem_fresh_a_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
+                                                                    uint64_t *__restrict__ O, uint64_t n,
+                                                                    const uint32_t *__restrict__ Tg) {
+    constexpr int WD = 8, WS = 4, WF = WD / 2 + 1;
+    extern __shared__ __align__(16) uint32_t smem32[];
+    __shared__ __align__(8) uint64_t bars[2];
+    uint32_t *T2 = smem32;                                                   // 256 * 4 * 2 rows of 4 words
+    uint64_t *tiles = reinterpret_cast<uint64_t *>(smem32 + 256 * 4 * 2 * 4); // [2 bufs][2 operands][MR_THREADS*WF]
+    const int tid = threadIdx.x;
+    for (uint32_t i = tid; i < 256u * 4u * 2u * 4u; i += MR_THREADS) {
+        const uint32_t w = i & 3, c = (i >> 2) & 1, k = (i >> 3) & 3, e = i >> 5;
+        (void)c;
+        T2[i] = Tg[(k * 256 + e) * WS + w];
+    }
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const FoldRot fr = fold_rot_init(T2, tid & 31);
+    constexpr uint32_t TILE_WORDS = MR_THREADS * WF;
+    const uint64_t nfull = n / MR_THREADS;
+    const uint64_t ntiles = (n + MR_THREADS - 1) / MR_THREADS;
+    if (tid == 0 && blockIdx.x < nfull) {
+        mbar_expect_tx(&bars[0], 2 * TILE_WORDS * 8);
+        tma_load_1d(tiles, A + (uint64_t)blockIdx.x * TILE_WORDS, TILE_WORDS * 8, &bars[0]);
+        tma_load_1d(tiles + TILE_WORDS, B + (uint64_t)blockIdx.x * TILE_WORDS, TILE_WORDS * 8, &bars[0]);
+    }
+    uint32_t it = 0;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        const uint64_t tn = t + gridDim.x;
+        if (tid == 0 && tn < nfull) {
+            uint64_t *dst = tiles + (size_t)(buf ^ 1) * 2 * TILE_WORDS;
+            mbar_expect_tx(&bars[buf ^ 1], 2 * TILE_WORDS * 8);
+            tma_load_1d(dst, A + tn * TILE_WORDS, TILE_WORDS * 8, &bars[buf ^ 1]);
+            tma_load_1d(dst + TILE_WORDS, B + tn * TILE_WORDS, TILE_WORDS * 8, &bars[buf ^ 1]);
+        }
+        uint32_t xa[WD + 1], xb[WD + 1];
+        const uint64_t u = t * MR_THREADS + tid;
+        if (t < nfull) {
+            mbar_wait(&bars[buf], (it >> 1) & 1);
+            const uint64_t *sa = tiles + (size_t)buf * 2 * TILE_WORDS + (size_t)tid * WF;
+            const uint64_t *sb = sa + TILE_WORDS;
+#pragma unroll
+            for (int j = 0; j < WD / 2; ++j) {
+                const uint64_t x = sa[j], y = sb[j];
+                xa[2 * j] = (uint32_t)x; xa[2 * j + 1] = (uint32_t)(x >> 32);
+                xb[2 * j] = (uint32_t)y; xb[2 * j + 1] = (uint32_t)(y >> 32);
+            }
+            xa[WD] = (uint32_t)sa[WD / 2] & 1u;
+            xb[WD] = (uint32_t)sb[WD / 2] & 1u;
+        } else { // ragged last tile: straight from global
+#pragma unroll
+            for (int j = 0; j <= WD; ++j) xa[j] = xb[j] = 0;
+            if (u < n) {
+                const uint64_t *ga = A + u * WF, *gb = B + u * WF;
+#pragma unroll
+                for (int j = 0; j < WD / 2; ++j) {
+                    const uint64_t x = ga[j], y = gb[j];
+                    xa[2 * j] = (uint32_t)x; xa[2 * j + 1] = (uint32_t)(x >> 32);
+                    xb[2 * j] = (uint32_t)y; xb[2 * j + 1] = (uint32_t)(y >> 32);
+                }
+                xa[WD] = (uint32_t)ga[WD / 2] & 1u;
+                xb[WD] = (uint32_t)gb[WD / 2] & 1u;
+            }
+        }
+        // a mod S, b mod S (two independent fold chains), top word first
+#pragma unroll
+        for (int i = WD; i >= WS; --i) {
+            uint32_t da[WS], db[WS];
+#pragma unroll
+            for (int q = 0; q < WS; ++q) {
+                da[q] = xa[i - WS + q];
+                db[q] = xb[i - WS + q];
+            }
+            fold_word_rot(da, xa[i], fr);
+            fold_word_rot(db, xb[i], fr);
+#pragma unroll
+            for (int q = 0; q < WS; ++q) {
+                xa[i - WS + q] = da[q];
+                xb[i - WS + q] = db[q];
+            }
+        }
+        uint32_t ra[WS], rb[WS], pq[2 * WS];
+#pragma unroll
+        for (int q = 0; q < WS; ++q) {
+            ra[q] = xa[q];
+            rb[q] = xb[q];
+        }
+        clmul_kara<WS>(ra, rb, pq);
+#pragma unroll
+        for (int i = 2 * WS - 1; i >= WS; --i) {
+            uint32_t dst[WS];
+#pragma unroll
+            for (int q = 0; q < WS; ++q) dst[q] = pq[i - WS + q];
+            fold_word_rot(dst, pq[i], fr);
+#pragma unroll
+            for (int q = 0; q < WS; ++q) pq[i - WS + q] = dst[q];
+        }
+        if (u < n) *reinterpret_cast<uint4 *>(O + u * (WS / 2)) = make_uint4(pq[0], pq[1], pq[2], pq[3]);
         __syncthreads(); // everyone is done with tiles[buf] before it is refilled
     }
 }
@@ -2165,6 +2365,106 @@ __global__ void __launch_bounds__(MR32_THREADS, 1) mulrem_fresh32_kernel(const u
             const int w = i - WS;
             r[0] = pw[(w >> 1) * TH * 2 + (w & 1)];
             if (top) fold_word<WS, 1, RS>(r, top, T);
+        }
+        uint32_t *out = reinterpret_cast<uint32_t *>(O + u * (WS / 2));
+#pragma unroll
+        for (int q = 0; q < WS / 4; ++q) reinterpret_cast<uint4 *>(out)[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    }
+}
+
+// K5d  config B fused mul+rem with the operands reduced first: (a b) mod S = ((a mod S)(b mod S)) mod S, so the product is
+// 16 x 16 words (three 8x8-word Karatsubas) instead of 32 x 32 (nine).  Same shared-memory columns and sliding-window fold
+// as mulrem_fresh32_kernel; the fold code exists once and runs three times (a, b, the product) from a phase loop.
+template <int STRIDE>
+__device__ __forceinline__ void mul16_acc_ss(const uint2 *__restrict__ m, const uint2 *__restrict__ c, uint32_t (&t)[32]) {
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) { // 0: low blocks, 1: high blocks, 2: (low + high) blocks
+        uint32_t x[8], y[8], r[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint2 u = make_uint2(0, 0), w = make_uint2(0, 0);
+            if (i != 1) {
+                const uint2 u0 = m[q * STRIDE], w0 = c[q * STRIDE];
+                u.x ^= u0.x; u.y ^= u0.y; w.x ^= w0.x; w.y ^= w0.y;
+            }
+            if (i != 0) {
+                const uint2 u1 = m[(4 + q) * STRIDE], w1 = c[(4 + q) * STRIDE];
+                u.x ^= u1.x; u.y ^= u1.y; w.x ^= w1.x; w.y ^= w1.y;
+            }
+            x[2 * q] = u.x; x[2 * q + 1] = u.y;
+            y[2 * q] = w.x; y[2 * q + 1] = w.y;
+        }
+        clmul_kara<8>(x, y, r);
+        if (i == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { t[q] ^= r[q]; t[8 + q] ^= r[q]; }
+        } else if (i == 1) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) { t[16 + q] ^= r[q]; t[8 + q] ^= r[q]; }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) t[8 + q] ^= r[q];
+        }
+    }
+}
+
+template <int WS>
+__global__ void __launch_bounds__(MR32_THREADS, 1) mulrem_fresh32r_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
+                                                                       uint64_t *__restrict__ O, uint64_t n,
+                                                                       const uint32_t *__restrict__ Tg) {
+    static_assert(WS == 16, "the product stage is written for d = 512");
+    constexpr int WD = 32, WF = WD / 2 + 1, TH = MR32_THREADS;
+    constexpr int RS = mulrem32_row_stride<WS>();
+    extern __shared__ __align__(16) uint32_t smem32[];
+    uint32_t *T = smem32;
+    uint2 *col = reinterpret_cast<uint2 *>(smem32 + 4 * 256 * RS) + threadIdx.x; // pair q of this thread at col[q * TH]
+    for (uint32_t i = threadIdx.x; i < 4u * 256u * WS; i += TH) T[(i / WS) * RS + (i % WS)] = Tg[i];
+    __syncthreads();
+    const uint32_t scol = (uint32_t)__cvta_generic_to_shared(col);
+    for (uint64_t u = (uint64_t)blockIdx.x * TH + threadIdx.x; u < n; u += (uint64_t)gridDim.x * TH) {
+        const uint64_t *ga = A + u * WF, *gb = B + u * WF;
+#pragma unroll
+        for (int q = 0; q < WF; ++q) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(scol + q * TH * 8), "l"(ga + q) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(scol + (WF + q) * TH * 8), "l"(gb + q) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        uint32_t r[WS];
+#pragma unroll 1
+        for (int ph = 0; ph < 3; ++ph) {
+            // phase 0: a (33 words from pair 0), 1: b (33 words from pair 17), 2: the product (32 words from pair 0)
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(col + (ph == 1 ? WF * TH : 0)); // word i at pw[(i / 2) * TH * 2 + (i & 1)]
+            const int N = ph == 2 ? 2 * WS : WD + 1;
+#pragma unroll
+            for (int q = 0; q < WS; ++q) {
+                const int w = N - 1 - WS + q;
+                r[q] = pw[(w >> 1) * TH * 2 + (w & 1)];
+            }
+            uint32_t top = pw[((N - 1) >> 1) * TH * 2 + ((N - 1) & 1)];
+            if (ph != 2) top &= 1u; // the X^1024 coefficient
+            if (top) fold_word<WS, 1, RS>(r, top, T);
+#pragma unroll 16
+            for (int i = N - 2; i >= WS; --i) {
+                top = r[WS - 1];
+#pragma unroll
+                for (int q = WS - 1; q > 0; --q) r[q] = r[q - 1];
+                const int w = i - WS;
+                r[0] = pw[(w >> 1) * TH * 2 + (w & 1)];
+                if (top) fold_word<WS, 1, RS>(r, top, T);
+            }
+            if (ph == 2) break;
+            uint2 *dst = col + (ph == 1 ? WF * TH : 0); // the reduced operand replaces the low words of the operand
+#pragma unroll
+            for (int q = 0; q < WS / 2; ++q) dst[q * TH] = make_uint2(r[2 * q], r[2 * q + 1]);
+            if (ph == 1) {
+                uint32_t t[2 * WS];
+#pragma unroll
+                for (int i = 0; i < 2 * WS; ++i) t[i] = 0;
+                mul16_acc_ss<TH>(col, col + WF * TH, t);
+#pragma unroll
+                for (int q = 0; q < WS; ++q) col[q * TH] = make_uint2(t[2 * q], t[2 * q + 1]);
+            }
         }
         uint32_t *out = reinterpret_cast<uint32_t *>(O + u * (WS / 2));
 #pragma unroll

@@ -19,15 +19,22 @@ cudaError_t launch_mulrem_fresh_b(const uint64_t *A, const uint64_t *B, uint64_t
 
 // rolled-product kernel (mulrem_fresh32_kernel): one 512-thread CTA per SM
 cudaError_t launch_mulrem_fresh_b32(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
-                                    int sm_count, cudaStream_t stream) {
+                                    int sm_count, cudaStream_t stream, bool reduce_first) {
     constexpr int WS = 16;
     const size_t smem = mulrem32_smem_bytes<WS>();
-    auto kern = mulrem_fresh32_kernel<WS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     uint64_t blocks = (pairs + MR32_THREADS - 1) / MR32_THREADS;
     if (blocks > (uint64_t)sm_count) blocks = (uint64_t)sm_count;
-    kern<<<(unsigned)blocks, MR32_THREADS, smem, stream>>>(A, B, O, pairs, Tg);
+    if (reduce_first) {
+        auto kern = mulrem_fresh32r_kernel<WS>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)blocks, MR32_THREADS, smem, stream>>>(A, B, O, pairs, Tg);
+    } else {
+        auto kern = mulrem_fresh32_kernel<WS>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)blocks, MR32_THREADS, smem, stream>>>(A, B, O, pairs, Tg);
+    }
     return cudaGetLastError();
 }
 } // namespace hmk
