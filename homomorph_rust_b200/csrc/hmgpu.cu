@@ -2244,11 +2244,16 @@ int hm_poly_mulrem(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_bat
         *out = o;
         return HM_OK;
     }
-    hm_batch *prod = nullptr;
-    int rc = hm_poly_mul(ctx, a, b, &prod);
-    if (rc != HM_OK) return rc;
-    rc = hm_poly_rem(ctx, prod, out);
-    hm_batch_free(ctx, prod);
+    // any other shapes: rem(mul(a, b)) = rem(mul(rem(a), rem(b))) — the remainder is unique — so the product is never wider
+    // than 2 d bits however long the operands are (a u32 sum times another is 23 552 x 23 552 bits otherwise)
+    hm_batch *ra = nullptr, *rb = nullptr, *prod = nullptr;
+    int rc = hm_poly_rem(ctx, a, &ra);
+    if (rc == HM_OK) rc = hm_poly_rem(ctx, b, &rb);
+    if (rc == HM_OK) rc = hm_poly_mul(ctx, ra, rb, &prod);
+    if (rc == HM_OK) rc = hm_poly_rem(ctx, prod, out);
+    if (ra) hm_batch_free(ctx, ra);
+    if (rb) hm_batch_free(ctx, rb);
+    if (prod) hm_batch_free(ctx, prod);
     return rc;
 }
 

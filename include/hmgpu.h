@@ -213,7 +213,9 @@ int hm_apply2_host(hm_context *ctx, int op, size_t n, uint32_t L, const uint32_t
 /* ---- Raw polynomial batches (L = 1) -------------------------------------------------------
  * Polynomial::add / mul / rem over batches — src/polynomial.rs:190-213, :252-310, :316-365.
  * rem is by the context's secret key S (the only divisor on the hot path, src/cipher.rs:120);
- * mulrem is the fused `(a*b) mod S` unit of BASELINE.json's second metric. */
+ * mulrem is the fused `(a*b) mod S` unit of BASELINE.json's second metric: the output is the remainder the reference's
+ * rem(mul(a, b)) gives, bit for bit; internally both operands are reduced mod S first (the remainder is unique), so the
+ * product is never wider than 2 d bits. */
 int hm_poly_add(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out);
 int hm_poly_mul(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch **out);
 int hm_poly_rem(hm_context *ctx, const hm_batch *a, hm_batch **out);

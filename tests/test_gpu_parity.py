@@ -587,6 +587,26 @@ def test_add_u128(oracle, hm):
     assert tuple(dec[0]) == (0, 0)
 
 
+def test_mulrem_on_sums(oracle, hm):
+    """mul+rem of non-fresh operands (two u8 sums: slot k has degree bound (3k-1) D): the generic path reduces both operands
+    first — rem(mul(a, b)) = rem(mul(rem(a), rem(b))) — and must still equal the oracle's literal mul then rem."""
+    rng = np.random.default_rng(61)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 9)
+    n, L = 11, 8
+    vals = [rng.integers(0, 256, size=n, dtype=np.uint8) for _ in range(4)]
+    ms = [masks_for(rng, n, L, CONFIG_A[3]) for _ in range(4)]
+    cs = [ctx.encrypt(v, m) for v, m in zip(vals, ms)]
+    os_ = [oracle_encrypt(oracle, pk, v, m) for v, m in zip(vals, ms)]
+    s1 = ctx.apply2(hm.HomomorphicAddition, cs[0], cs[1])
+    s2 = ctx.apply2(hm.HomomorphicAddition, cs[2], cs[3])
+    w1, _ = oracle.apply(oracle.OP_ADD, os_[0], os_[1], L, threads=oracle.max_threads())
+    w2, _ = oracle.apply(oracle.OP_ADD, os_[2], os_[3], L, threads=oracle.max_threads())
+    r = ctx.poly_mulrem(s1, s2)
+    want, _ = oracle.poly_mulrem(w1, w2, sk, threads=oracle.max_threads())
+    np.testing.assert_array_equal(r.to_host(), expected_padded(want, n, r.slot_words()))
+    np.testing.assert_array_equal(ctx.poly_rem(ctx.poly_mul(s1, s2)).to_host(), r.to_host())
+
+
 def test_empty_batches(oracle, hm):
     """n = 0 everywhere (the reference's Vec-based API accepts empty inputs)."""
     sk, pk, ctx = setup(oracle, hm, CONFIG_A, 2)
