@@ -1367,6 +1367,7 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mulrem_fresh_a_kernel(const uin
     }
     __syncthreads();
     const FoldRot fr = fold_rot_init(T2, tid & 31);
+    const uint32_t krow = (uint32_t)__cvta_generic_to_shared(T2) + ((1 * 4 + 0) * 2 + 0) * 16; // row (byte 1, table 0, copy 0)
     constexpr uint32_t TILE_WORDS = MR_THREADS * WF;
     const uint64_t nfull = n / MR_THREADS;
     const uint64_t ntiles = (n + MR_THREADS - 1) / MR_THREADS;
@@ -1414,9 +1415,17 @@ __global__ void __launch_bounds__(MR_THREADS, 1) mulrem_fresh_a_kernel(const uin
                 xb[WD] = (uint32_t)gb[WD / 2] & 1u;
             }
         }
-        // a mod S, b mod S (two independent fold chains), top word first
+        // a mod S, b mod S (two independent fold chains), top down.  The top "word" is the single coefficient of X^256:
+        // its fold is one row (table 0, byte 1 = X^256 mod S; every lane reads the same address, a broadcast) under a mask.
+        {
+            uint32_t k0, k1, k2, k3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(k0), "=r"(k1), "=r"(k2), "=r"(k3) : "r"(krow));
+            const uint32_t ma = 0u - xa[WD], mb = 0u - xb[WD];
+            xa[WD - 4] ^= k0 & ma; xa[WD - 3] ^= k1 & ma; xa[WD - 2] ^= k2 & ma; xa[WD - 1] ^= k3 & ma;
+            xb[WD - 4] ^= k0 & mb; xb[WD - 3] ^= k1 & mb; xb[WD - 2] ^= k2 & mb; xb[WD - 1] ^= k3 & mb;
+        }
 #pragma unroll
-        for (int i = WD; i >= WS; --i) {
+        for (int i = WD - 1; i >= WS; --i) {
             uint32_t da[WS], db[WS];
 #pragma unroll
             for (int q = 0; q < WS; ++q) {
