@@ -454,13 +454,13 @@ def run_ours(args, rank, local_rank, world):
         ctxb.synchronize()
         sb = e0.elapsed_time(e1) * 1e-3 / 5
         extra["mulrem_config_b"] = {"metric": "GF(2)[X] mul+rem/s (d=d'=512, tau=256, delta=8)", "value": nb * 8 / sb, "unit": "mul+rem/s",
-                                    "kernel": "mulrem_fresh32r_kernel<16>", "pairs_per_launch": nb * 8, "ms": sb * 1e3,
+                                    "kernel": "mulrem_fresh32q_kernel", "pairs_per_launch": nb * 8, "ms": sb * 1e3,
                                     "Tbitmac_per_s": nb * 8 * (1050625 + 788481) / sb / 1e12,
                                     "alu_frac": nb * 8 * (1050625 + 788481) / sb / (lane_ops.value * 32.0),
                                     "product_pipe_frac": 3 * nb * 8 / sb / k8m.value,  # three 8x8-word products per pair (+ the table folds)
                                     "note": "operands reduced mod S first (sliding-window table folds from shared memory), then a 16-word product "
                                             "(three 8x8-word Karatsubas) and one more fold; the fully unrolled first kernel did 275 M/s, the rolled "
-                                            "32-word product followed by one fold 720 M/s"}
+                                            "32-word product followed by one fold 720 M/s, reduce-first with conflicting table lookups 1.2-1.35 G/s"}
         for ob in (cb1, cb2, mrb):
             ob.free()
         ctxb.close()

@@ -2481,6 +2481,99 @@ __global__ void __launch_bounds__(MR32_THREADS, 1) mulrem_fresh32r_kernel(const 
     }
 }
 
+// K5e  mulrem_fresh32r_kernel with a conflict-free fold table (ncu on K5d: shared-memory wavefronts 88 % busy, 54 % of them
+// bank conflicts).  Same rotation as config A: lane l does the four byte lookups of a fold in the order k = (q + l) % 4 and
+// chunk j of row (byte e, table k, copy c) sits at (((e * 4 + j) * 4 + k) * 2 + c) * 16 bytes, bank group 2 k + c for every
+// e and j; c = bit 2 of the lane.  The table is 128 KB, which fits because the operands are now loaded one after the other
+// into ONE set of 17 column pairs (a is reduced to 16 registers before b arrives).
+constexpr int MR32Q_PAIRS = 17;
+constexpr size_t MR32Q_SMEM_BYTES = (size_t)256 * 4 * 4 * 2 * 16 + (size_t)MR32Q_PAIRS * MR32_THREADS * 8;
+
+__device__ __forceinline__ void fold_word_rot16(uint32_t (&dst)[16], uint32_t t, const FoldRot &f) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t x[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t e;
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(e) : "r"(t), "r"(0u), "r"(f.sel[q]));
+            const uint32_t addr = e * 512u + f.off[q] + j * 128;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[q][0]), "=r"(x[q][1]), "=r"(x[q][2]), "=r"(x[q][3]) : "r"(addr));
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) dst[4 * j + w] ^= x[0][w] ^ x[1][w] ^ x[2][w] ^ x[3][w];
+    }
+}
+
+static __global__ void __launch_bounds__(MR32_THREADS, 1) mulrem_fresh32q_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
+                                                                              uint64_t *__restrict__ O, uint64_t n,
+                                                                              const uint32_t *__restrict__ Tg) {
+    constexpr int WS = 16, WD = 32, WF = WD / 2 + 1, TH = MR32_THREADS;
+    extern __shared__ __align__(16) uint32_t smem32[];
+    uint32_t *T2 = smem32; // 256 * 4 * 4 * 2 rows of 4 words
+    uint2 *col = reinterpret_cast<uint2 *>(smem32 + 256 * 4 * 4 * 2 * 4) + threadIdx.x; // pair q of this thread at col[q * TH]
+    for (uint32_t i = threadIdx.x; i < 256u * 4u * 4u * 2u * 4u; i += TH) {
+        const uint32_t w = i & 3, k = (i >> 3) & 3, j = (i >> 5) & 3, e = i >> 7; // bit 2 = copy
+        T2[i] = Tg[(k * 256 + e) * WS + 4 * j + w];
+    }
+    __syncthreads();
+    const FoldRot fr = fold_rot_init(T2, threadIdx.x & 31);
+    const uint32_t scol = (uint32_t)__cvta_generic_to_shared(col);
+    for (uint64_t u = (uint64_t)blockIdx.x * TH + threadIdx.x; u < n; u += (uint64_t)gridDim.x * TH) {
+        uint32_t r[WS], ra[WS];
+#pragma unroll 1
+        for (int ph = 0; ph < 3; ++ph) {
+            // phase 0: a (33 words), 1: b (33 words), 2: the product (32 words); all of them in column pairs 0..16
+            if (ph < 2) {
+                const uint64_t *g = (ph == 0 ? A : B) + u * WF;
+#pragma unroll
+                for (int q = 0; q < WF; ++q)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(scol + q * TH * 8), "l"(g + q) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(col); // word i at pw[(i / 2) * TH * 2 + (i & 1)]
+            const int N = ph == 2 ? 2 * WS : WD + 1;
+#pragma unroll
+            for (int q = 0; q < WS; ++q) {
+                const int w = N - 1 - WS + q;
+                r[q] = pw[(w >> 1) * TH * 2 + (w & 1)];
+            }
+            uint32_t top = pw[((N - 1) >> 1) * TH * 2 + ((N - 1) & 1)];
+            if (ph != 2) top &= 1u; // the X^1024 coefficient
+            fold_word_rot16(r, top, fr);
+#pragma unroll 16
+            for (int i = N - 2; i >= WS; --i) {
+                top = r[WS - 1];
+#pragma unroll
+                for (int q = WS - 1; q > 0; --q) r[q] = r[q - 1];
+                const int w = i - WS;
+                r[0] = pw[(w >> 1) * TH * 2 + (w & 1)];
+                fold_word_rot16(r, top, fr);
+            }
+            if (ph == 0) {
+#pragma unroll
+                for (int q = 0; q < WS; ++q) ra[q] = r[q];
+            } else if (ph == 1) {
+#pragma unroll
+                for (int q = 0; q < WS / 2; ++q) {
+                    col[q * TH] = make_uint2(ra[2 * q], ra[2 * q + 1]);
+                    col[(8 + q) * TH] = make_uint2(r[2 * q], r[2 * q + 1]);
+                }
+                uint32_t t[2 * WS];
+#pragma unroll
+                for (int i = 0; i < 2 * WS; ++i) t[i] = 0;
+                mul16_acc_ss<TH>(col, col + 8 * TH, t);
+#pragma unroll
+                for (int q = 0; q < WS; ++q) col[q * TH] = make_uint2(t[2 * q], t[2 * q + 1]);
+            }
+        }
+        uint32_t *out = reinterpret_cast<uint32_t *>(O + u * (WS / 2));
+#pragma unroll
+        for (int q = 0; q < WS / 4; ++q) reinterpret_cast<uint4 *>(out)[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 // LOP3 issue-rate probe: the measured denominator of the integer-logic roofline.
 // 8 independent dependency chains per thread, 8 warps per CTA, 8 CTAs per SM.
