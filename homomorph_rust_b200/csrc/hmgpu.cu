@@ -22,8 +22,6 @@
 #include "kernels.cuh"
 
 namespace hmk {
-cudaError_t launch_mulrem_fresh_b(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
-                                  int sm_count, cudaStream_t stream); // kernels_b.cu
 cudaError_t launch_mulrem_fresh_b32(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
                                     int sm_count, cudaStream_t stream, int reduce_first); // kernels_b.cu
 }
@@ -2179,11 +2177,10 @@ static int mulrem_fresh_exec(hm_context *ctx, const hm_batch *a, const hm_batch 
     const uint64_t pairs = (uint64_t)a->n * a->L;
     if (!pairs) return HM_OK;
     if (ctx->fresh_deg == 1024) {
-        // 0 = fully unrolled first kernel, 1 = rolled 32-word product then fold, 2 = operands reduced first (16-word product),
-        // 3 = reduce-first with the conflict-free rotated fold table
+        // 1 = rolled 32-word product then fold, 2 = operands reduced first (16-word product), 3 = reduce-first with the
+        // conflict-free rotated fold table
         static const int mode_b = getenv("HM_MULREM_B_MODE") ? atoi(getenv("HM_MULREM_B_MODE")) : 3;
-        if (mode_b) CK(hmk::launch_mulrem_fresh_b32(a->d, b->d, o->d, pairs, ctx->d_remT, ctx->sm_count, ctx->stream, mode_b - 1));
-        else CK(hmk::launch_mulrem_fresh_b(a->d, b->d, o->d, pairs, ctx->d_remT, ctx->sm_count, ctx->stream));
+        CK(hmk::launch_mulrem_fresh_b32(a->d, b->d, o->d, pairs, ctx->d_remT, ctx->sm_count, ctx->stream, mode_b < 1 ? 0 : mode_b - 1));
         ctx->launches++;
         return HM_OK;
     }

@@ -1,22 +1,9 @@
-// kernels_b.cu — the d = d' = 512 (D = 1024) instantiation of the fused mul+rem kernel, in its own translation unit
-// because the fully unrolled 32-word Karatsuba takes ptxas a couple of minutes.
+// kernels_b.cu — the d = d' = 512 (D = 1024) fused mul+rem kernels, in their own translation unit (compiled in parallel
+// with hmgpu.cu).  The first version, a fully unrolled 32-word Karatsuba (243 inlined leaf products, two minutes of ptxas,
+// 275 M mul+rem/s), is gone; its successors are rolled.
 #include "kernels.cuh"
 
 namespace hmk {
-cudaError_t launch_mulrem_fresh_b(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
-                                  int sm_count, cudaStream_t stream) {
-    constexpr int WD = 32, WS = 16, TH = 128;
-    const size_t smem = (size_t)4 * 256 * WS * 4 + (size_t)2 * 2 * TH * (WD / 2 + 1) * 8;
-    auto kern = mulrem_fresh_kernel<WD, WS, 2, TH, 1>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    uint64_t blocks = (pairs + TH - 1) / TH;
-    const uint64_t cap = (uint64_t)sm_count * 2;
-    if (blocks > cap) blocks = cap;
-    kern<<<(unsigned)blocks, TH, smem, stream>>>(A, B, O, pairs, Tg);
-    return cudaGetLastError();
-}
-
 // rolled-product kernel (mulrem_fresh32_kernel): one 512-thread CTA per SM
 cudaError_t launch_mulrem_fresh_b32(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
                                     int sm_count, cudaStream_t stream, int reduce_first) {
