@@ -15,6 +15,7 @@ from oracle import hmoracle as orc  # noqa: E402
 
 A = (128, 128, 1, 128)
 ok = True
+SEED = int(os.environ.get("SOAK_SEED", "42"))  # keys, plaintexts and masks all derive from it
 
 
 def check(name, got, want, t0):
@@ -25,13 +26,14 @@ def check(name, got, want, t0):
 
 
 def rb(seed, n):
-    return np.frombuffer(np.random.default_rng(seed).bytes(n), dtype=np.uint8)
+    return np.frombuffer(np.random.default_rng(seed + 1000 * SEED).bytes(n), dtype=np.uint8)
 
 
-sk, pk, skb, pkb = keys(orc, *A, 777)
+print(f"# soak seed {SEED}", flush=True)
+sk, pk, skb, pkb = keys(orc, *A, 777 + SEED)
 ctx = engine_context(hm, *A, skb, pkb)
 lib = hm.lib()
-rng = np.random.default_rng(42)
+rng = np.random.default_rng(SEED)
 T = orc.max_threads()
 
 # encrypt / decrypt
@@ -85,7 +87,7 @@ for op, oop, nm in ((hm.HomomorphicAndGate, orc.OP_AND, "AND"), (hm.HomomorphicO
 # config B (d = d' = 512, tau = 256, delta = 8): table encrypt, fused mul+rem, regrouped generic adder
 del ctx
 B = (512, 512, 8, 256)
-sk, pk, skb, pkb = keys(orc, *B, 778)
+sk, pk, skb, pkb = keys(orc, *B, 778 + SEED)
 ctx = engine_context(hm, *B, skb, pkb)
 t0 = time.time(); n = 20_000
 a = rng.integers(0, 256, size=n, dtype=np.uint8); b = rng.integers(0, 256, size=n, dtype=np.uint8)
