@@ -401,6 +401,9 @@ def run_ours(args, rank, local_rank, world):
         extra["and_gate"] = {"value": n * L / s, "unit": "bit-ciphertext ands/s", "kernel": "mul_small_kernel<8,8>", "ms": s * 1e3,
                              "hbm_GBps": n * L * 152 / s / 1e9, "Tbitmac_per_s": n * L * 66049 / s / 1e12,
                              "alu_frac": n * L * 66049 / s / (lane_ops.value * 32.0)}
+        s = timed(lambda: lib.hm_apply2_into(ctx._h, N.HM_OP_OR, ca._h, cb._h, ao._h), reps=5)
+        extra["or_gate"] = {"value": n * L / s, "unit": "bit-ciphertext ors/s", "kernel": "mul_small_kernel<8,8> (a + b + a*b fused)", "ms": s * 1e3,
+                            "hbm_GBps": n * L * 152 / s / 1e9}
         ao.free()
         # config 4: u8 homomorphic multiply (column circuit, common.rs:66-105) on 2^14 pairs, then decrypt
         n8 = 1 << 14

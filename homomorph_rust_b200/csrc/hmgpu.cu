@@ -306,7 +306,7 @@ int launch_xor_views(hm_context *ctx, View o, View a, View b, size_t n);
 View null_view();
 
 int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *h_ops, size_t cnt, size_t n, size_t smem_general,
-                     uint32_t per_warp_general, bool outputs_zeroed) {
+                     uint32_t per_warp_general, bool outputs_zeroed, int fuse_or) {
     // thread-per-chunk kernels: chunks of the shorter operand (32-word chunks see "low words + top coefficient" operands)
     const bool chunk32 = g_mul_thread_chunk != 24;
     uint32_t xchunks_max = 0;
@@ -318,10 +318,10 @@ int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *
     }
     const dim3 grid_t((unsigned)((n + 127) / 128), (unsigned)cnt);
     switch (cls) {
-        case 808: hmk::mul_small_kernel<8, 8><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
-        case 1616: hmk::mul_small_kernel<16, 16><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
-        case 1632: hmk::mul_small_kernel<16, 32><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
-        case 3216: hmk::mul_small_kernel<32, 16><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n); break;
+        case 808: hmk::mul_small_kernel<8, 8><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n, fuse_or); break;
+        case 1616: hmk::mul_small_kernel<16, 16><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n, fuse_or); break;
+        case 1632: hmk::mul_small_kernel<16, 32><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n, fuse_or); break;
+        case 3216: hmk::mul_small_kernel<32, 16><<<grid_t, 128, 0, ctx->stream>>>(d_ops, n, fuse_or); break;
         default: {
             // enough (value, chunk) pairs to fill the GPU with one thread each?  -> Karatsuba thread kernel
             static const int no_thread = getenv("HM_MUL_NO_THREAD") ? atoi(getenv("HM_MUL_NO_THREAD")) : 0;
@@ -360,7 +360,9 @@ int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *
     return post_launch(ctx, "mul kernel");
 }
 
-int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n, bool outputs_zeroed = false) {
+// fused_or: in/out.  On entry non-zero asks for a + b + a*b; on return it says whether every product went through a kernel
+// that fused it (the caller adds a and b itself otherwise).
+int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n, bool outputs_zeroed = false, int *fused_or = nullptr) {
     if (ops_in.empty() || n == 0) return HM_OK;
     // group by shape class (stable), one launch per class
     std::vector<MulOp> ops(ops_in);
@@ -375,6 +377,12 @@ int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n, 
     for (size_t i = 0; i < order.size(); ++i) {
         sorted[i] = ops[order[i]];
         scls[i] = cls[order[i]];
+    }
+    int fuse_or = 0;
+    if (fused_or && *fused_or) { // only the register-resident kernels can fuse the two extra XORs
+        fuse_or = 1;
+        for (int c : scls) fuse_or &= (c != 0);
+        *fused_or = fuse_or;
     }
     size_t slot = 0;
     int rc = ensure_ops(ctx, sorted.size(), &slot);
@@ -399,7 +407,7 @@ int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n, 
             if (smem > ctx->smem_optin) return HM_ERR_UNSUPPORTED;
         }
         rc = launch_mul_class(ctx, scls[first], ctx->d_ops + slot + first, sorted.data() + first, last - first, n, smem, per_warp,
-                              outputs_zeroed);
+                              outputs_zeroed, fuse_or);
         if (rc != HM_OK) return rc;
         first = last;
     }
@@ -1826,16 +1834,18 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                 vb.stride = vb.w;
                 vo.stride = vo.w;
                 ops.push_back(MulOp{va, vb, vo});
-                rc = launch_mul_ops(ctx, ops, n * a->L);
-                if (rc == HM_OK && op == HM_OP_OR) {
+                int fused = op == HM_OP_OR;
+                rc = launch_mul_ops(ctx, ops, n * a->L, false, &fused);
+                if (rc == HM_OK && op == HM_OP_OR && !fused) {
                     rc = launch_xor_views(ctx, vo, vo, va, n * a->L);
                     if (rc == HM_OK) rc = launch_xor_views(ctx, vo, vo, vb, n * a->L);
                 }
                 break;
             }
             for (uint32_t k = 0; k < a->L; ++k) ops.push_back(MulOp{slot_view(a, k), slot_view(b, k), slot_view(o, k)});
-            rc = launch_mul_ops(ctx, ops, n);
-            if (rc == HM_OK && op == HM_OP_OR) { // a + b + a*b, cipher.rs:76-83
+            int fused = op == HM_OP_OR;
+            rc = launch_mul_ops(ctx, ops, n, false, &fused);
+            if (rc == HM_OK && op == HM_OP_OR && !fused) { // a + b + a*b, cipher.rs:76-83
                 for (uint32_t k = 0; k < a->L && rc == HM_OK; ++k) {
                     View ok = slot_view(o, k);
                     rc = launch_xor_views(ctx, ok, ok, slot_view(a, k), n);

@@ -861,7 +861,7 @@ __device__ __forceinline__ void clmul_kara(const uint32_t (&a)[N], const uint32_
 // early carries of the multiplier circuit.
 // ----------------------------------------------------------------------------------------
 template <int NX, int NY>
-__global__ void __launch_bounds__(128) mul_small_kernel(const MulOp *__restrict__ ops, uint64_t n) {
+__global__ void __launch_bounds__(128) mul_small_kernel(const MulOp *__restrict__ ops, uint64_t n, int fuse_or = 0) {
     constexpr int K = (NX == 8) ? 8 : 16; // Karatsuba block
     static_assert(NX % K == 0 && NY % K == 0, "operands are whole blocks");
     const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -907,6 +907,14 @@ __global__ void __launch_bounds__(128) mul_small_kernel(const MulOp *__restrict_
 #pragma unroll
     for (int j = 0; j < NX; ++j) r[NY + j] ^= x[j] & my;
     r[NX + NY] ^= xt & yt;
+    if (fuse_or) { // gate_or = a + b + a*b (src/cipher.rs:76-83): the operands are still in registers
+#pragma unroll
+        for (int j = 0; j < NX; ++j) r[j] ^= x[j];
+#pragma unroll
+        for (int j = 0; j < NY; ++j) r[j] ^= y[j];
+        r[NX] ^= xt;
+        r[NY] ^= yt;
+    }
     uint64_t *go = op.o.base + v * op.o.stride + op.o.off;
 #pragma unroll
     for (int j = 0; j < (NX + NY) / 2 + 1; ++j)
