@@ -2526,6 +2526,7 @@ static __global__ void __launch_bounds__(MR32_THREADS, 1) mulrem_fresh32q_kernel
     }
     __syncthreads();
     const FoldRot fr = fold_rot_init(T2, threadIdx.x & 31);
+    const uint32_t krow = (uint32_t)__cvta_generic_to_shared(T2) + 512; // row (byte 1, chunk 0, table 0, copy 0); chunk j is 128 j further
     const uint32_t scol = (uint32_t)__cvta_generic_to_shared(col);
     for (uint64_t u = (uint64_t)blockIdx.x * TH + threadIdx.x; u < n; u += (uint64_t)gridDim.x * TH) {
         uint32_t r[WS], ra[WS];
@@ -2548,8 +2549,17 @@ static __global__ void __launch_bounds__(MR32_THREADS, 1) mulrem_fresh32q_kernel
                 r[q] = pw[(w >> 1) * TH * 2 + (w & 1)];
             }
             uint32_t top = pw[((N - 1) >> 1) * TH * 2 + ((N - 1) & 1)];
-            if (ph != 2) top &= 1u; // the X^1024 coefficient
-            fold_word_rot16(r, top, fr);
+            if (ph != 2) { // the X^1024 coefficient: one row (byte 1 of table 0 = X^1024 mod S, same address in every lane) under a mask
+                const uint32_t mask = 0u - (top & 1u);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    uint32_t k0, k1, k2, k3;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(k0), "=r"(k1), "=r"(k2), "=r"(k3) : "r"(krow + jj * 128));
+                    r[4 * jj] ^= k0 & mask; r[4 * jj + 1] ^= k1 & mask; r[4 * jj + 2] ^= k2 & mask; r[4 * jj + 3] ^= k3 & mask;
+                }
+            } else {
+                fold_word_rot16(r, top, fr);
+            }
 #pragma unroll 16
             for (int i = N - 2; i >= WS; --i) {
                 top = r[WS - 1];
