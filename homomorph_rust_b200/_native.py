@@ -24,13 +24,14 @@ HM_ERR_CUDA = -6
 HM_ERR_UNSUPPORTED = -7
 HM_ERR_INVALID_ARGUMENT = -8
 HM_ERR_DIVIDE_BY_ZERO = -9
+HM_ERR_OUT_OF_MEMORY = -10
 
 HM_OP_AND, HM_OP_OR, HM_OP_XOR, HM_OP_NOT, HM_OP_ADD, HM_OP_MUL = range(6)
 
 
 def build(force: bool = False) -> str:
     """Compile csrc/ into libhmgpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("hmgpu.cu", "kernels_b.cu", "kernels.cuh", "gf2host.hpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("hmgpu.cu", "kernels_b.cu", "kernels_adder.cu", "kernels_adder.h", "kernels.cuh", "gf2_blocks.cuh", "gf2host.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "hmgpu.h"))
     stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
     if force or stale:
@@ -91,6 +92,8 @@ def lib() -> C.CDLL:
         "hm_batch_serialize": (C.c_int, [vp, vp, vp, sz]),
         "hm_batch_deserialize": (C.c_int, [vp, vp, sz, C.POINTER(vp)]),
         "hm_batch_download_canonical": (C.c_int, [vp, vp, vp, sz, C.POINTER(sz)]),
+        "hm_batch_upload_canonical": (C.c_int, [vp, sz, C.c_uint32, vp, sz, u64p, C.POINTER(vp)]),
+        "hm_batch_wire_inspect": (C.c_int, [vp, sz, C.POINTER(u16), u32p, u64p, u64p]),
         "hm_host_alloc": (vp, [sz]),
         "hm_host_free": (None, [vp]),
         "hm_encrypt": (C.c_int, [vp, vp, sz, C.c_uint32, vp, C.POINTER(vp)]),
@@ -111,6 +114,8 @@ def lib() -> C.CDLL:
         "hm_op_min_d_over_delta": (C.c_int, [C.c_int]),
         "hm_result_slot_words": (C.c_int, [vp, C.c_int, C.c_uint32, u32p, u32p, u32p]),
         "hm_apply2_host": (C.c_int, [vp, C.c_int, sz, C.c_uint32, u32p, vp, u32p, vp, vp]),
+        "hm_apply2_host_bounded": (C.c_int, [vp, C.c_int, sz, C.c_uint32, u64p, vp, u64p, vp, vp]),
+        "hm_result_slot_bounds": (C.c_int, [C.c_int, C.c_uint32, u64p, u64p, u64p]),
         "hm_poly_add": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
         "hm_poly_mul": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
         "hm_poly_rem": (C.c_int, [vp, vp, C.POINTER(vp)]),

@@ -225,6 +225,8 @@ def _check(ctx_handle, rc: int) -> None:
         raise InvalidCipheredLength("InvalidCipheredLength")
     if rc == N.HM_ERR_DIVIDE_BY_ZERO:
         raise ZeroDivisionError("attempt to divide by zero")
+    if rc == N.HM_ERR_OUT_OF_MEMORY:
+        raise MemoryError(detail or "out of host or device memory")
     raise EngineError(rc, detail)
 
 
@@ -324,9 +326,10 @@ class Ciphered:
             self._h = None
 
     def __del__(self):
+        # safe in either order: a batch whose context is already destroyed is an orphan (its device memory went with the
+        # context) and freeing it only releases the handle
         try:
-            if self._ctx._h is not None:
-                self.free()
+            self.free()
         except Exception:
             pass
 
@@ -517,6 +520,21 @@ class Context:
             db = np.asarray(degree_bounds, dtype=np.uint64)
             assert all(int(b) // 64 + 1 == int(w) for b, w in zip(db, slot_words))
             rc = N.lib().hm_batch_upload_bounded(self._h, n, L, db.ctypes.data_as(C.POINTER(C.c_uint64)), host.ctypes.data, C.byref(out))
+        _check(self._h, rc)
+        return Ciphered(self, out.value)
+
+    def upload_canonical(self, polys, n: int, bits: int, degree_bounds: Optional[Sequence[int]] = None) -> Ciphered:
+        """n * bits canonical polynomials [(degree, words)] (value-major, slot-minor) — e.g. exported by a Rust build of the
+        reference, or by Ciphered.canonical() — as a device batch: the inverse of Ciphered.canonical()."""
+        flat = []
+        for deg, words in polys:
+            flat.append(np.asarray([deg], dtype=np.uint64))
+            flat.append(np.asarray(words, dtype=np.uint64))
+        buf = np.ascontiguousarray(np.concatenate(flat) if flat else np.zeros(0, dtype=np.uint64))
+        out = C.c_void_p()
+        db = None if degree_bounds is None else np.asarray(degree_bounds, dtype=np.uint64)
+        rc = N.lib().hm_batch_upload_canonical(self._h, n, bits, buf.ctypes.data, buf.size,
+                                               None if db is None else db.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(out))
         _check(self._h, rc)
         return Ciphered(self, out.value)
 

@@ -15,11 +15,13 @@
 #include <cstring>
 #include <map>
 #include <new>
+#include <set>
 #include <string>
 #include <vector>
 
 #include "gf2host.hpp"
 #include "kernels.cuh"
+#include "kernels_adder.h"
 
 namespace hmk {
 cudaError_t launch_mulrem_fresh_b32(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
@@ -31,6 +33,9 @@ static long g_adder_thread_min = -1;
 static long g_mul_thread_min = -1; // minimum (values x chunks) for the thread-per-chunk multiply; < 0 = default (128 per SM)
 static long g_mul_thread_chunk = 32; // 24 = the first thread-per-chunk kernel (3-way Karatsuba chunks)
 static long g_mul_circuit_seq = 0;
+static long g_adder_chain = getenv("HM_ADDER_CHAIN") ? atol(getenv("HM_ADDER_CHAIN")) : 4;   // 0 = round-1 thread kernels; else 10 * (window in smem) + CTAs per SM
+static long g_adder_phases = getenv("HM_ADDER_PHASES") ? atol(getenv("HM_ADDER_PHASES")) : 4; // work units per value of the scheduled adder chain
+static long g_host_chunk_mb = getenv("HM_HOST_CHUNK_MB") ? atol(getenv("HM_HOST_CHUNK_MB")) : 96; // per-stage bytes of the host-buffer pipeline
 static long g_adder_generic_seq = 0; // 1 = the generic adder evaluates the reference's formula literally (two long products per bit)  // 1 = launch the multiplier circuit's carry products one by one (the first plan)
 
 using hmk::Layout;
@@ -89,6 +94,13 @@ struct hm_context {
     MulOp *h_ops = nullptr;
     size_t d_ops_cap = 0;
     size_t ops_cursor = 0;
+
+    // work queue of the dynamically scheduled adder chain (kernels_adder.cu): counter + one flag per 32 values
+    uint32_t *d_sched = nullptr;
+    size_t sched_words = 0;
+
+    cudaMemPool_t pool = nullptr;  // private stream-ordered pool: nothing process-wide is reconfigured
+    std::set<hm_batch *> live;     // batches still owned by callers; orphaned (device memory released) by hm_context_destroy
 };
 
 namespace {
@@ -106,6 +118,26 @@ int fail_cuda(hm_context *ctx, cudaError_t e, const char *what) {
         cudaError_t e__ = (call);                                  \
         if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
     } while (0)
+
+// stream-ordered allocation from the context's own pool, in ctx->stream order
+cudaError_t pool_alloc(hm_context *ctx, void **p, size_t bytes) {
+    if (ctx->pool) return cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream);
+    return cudaMallocAsync(p, bytes, ctx->stream);
+}
+template <typename T> cudaError_t pool_alloc(hm_context *ctx, T **p, size_t bytes) { return pool_alloc(ctx, reinterpret_cast<void **>(p), bytes); }
+
+// frees a pool allocation on every exit path of the enclosing scope (in the order of the stream it was allocated on)
+struct PoolGuard {
+    hm_context *ctx;
+    cudaStream_t stream;
+    void *p = nullptr;
+    explicit PoolGuard(hm_context *c) : ctx(c), stream(c->stream) {}
+    PoolGuard(const PoolGuard &) = delete;
+    PoolGuard &operator=(const PoolGuard &) = delete;
+    ~PoolGuard() {
+        if (p) cudaFreeAsync(p, stream);
+    }
+};
 
 int use_device(hm_context *ctx) {
     CK(cudaSetDevice(ctx->device));
@@ -132,15 +164,46 @@ Layout make_layout(const hm_batch *b) {
     return l;
 }
 
-hm_batch *new_batch(hm_context *ctx, size_t n, uint32_t L, const uint64_t *degb) {
+// Largest degree bound a slot may carry (result_bounds refuses anything above it too) and the widest value the 32-bit
+// slot offsets of the kernels' Layout can describe.
+constexpr uint64_t MAX_DEGREE_BOUND = (uint64_t)1 << 31;
+constexpr uint64_t MAX_VALUE_WORDS = ((uint64_t)1 << 32) - 1;
+
+// Sum of the slot widths of `degb`, or 0 if a bound or the sum is out of range.
+uint64_t checked_value_words(uint32_t L, const uint64_t *degb) {
+    uint64_t o = 0;
+    for (uint32_t k = 0; k < L; ++k) {
+        if (degb[k] > MAX_DEGREE_BOUND) return 0;
+        o += degb[k] / 64 + 1;
+        if (o > MAX_VALUE_WORDS) return 0;
+    }
+    return o;
+}
+
+// *status: HM_ERR_INVALID_ARGUMENT (bounds / sizes out of range) or HM_ERR_OUT_OF_MEMORY (host allocation failed)
+hm_batch *new_batch(hm_context *ctx, size_t n, uint32_t L, const uint64_t *degb, int *status = nullptr) {
+    int dummy;
+    int &st = status ? *status : dummy;
+    st = HM_ERR_INVALID_ARGUMENT;
+    if (L == 0 || L > (uint32_t)hmk::MAX_SLOTS) return nullptr;
+    const uint64_t vw = checked_value_words(L, degb);
+    if (vw == 0) return nullptr;
+    if (n > (SIZE_MAX / 8) / vw) return nullptr; // n * value_words * 8 must fit a size_t
+    st = HM_ERR_OUT_OF_MEMORY;
     hm_batch *b = new (std::nothrow) hm_batch;
     if (!b) return nullptr;
+    try {
+        b->w.resize(L);
+        b->off.resize(L + 1);
+        b->degb.assign(degb, degb + L);
+        ctx->live.insert(b);
+    } catch (const std::bad_alloc &) {
+        delete b;
+        return nullptr;
+    }
     b->ctx = ctx;
     b->n = n;
     b->L = L;
-    b->w.resize(L);
-    b->off.resize(L + 1);
-    b->degb.assign(degb, degb + L);
     uint64_t o = 0;
     for (uint32_t k = 0; k < L; ++k) {
         b->off[k] = (uint32_t)o;
@@ -149,19 +212,34 @@ hm_batch *new_batch(hm_context *ctx, size_t n, uint32_t L, const uint64_t *degb)
     }
     b->off[L] = (uint32_t)o;
     b->value_words = o;
+    st = HM_OK;
     return b;
+}
+
+// drops a batch that never got (or no longer has) device memory
+void discard_batch(hm_batch *b) {
+    if (!b) return;
+    if (b->ctx) b->ctx->live.erase(b);
+    delete b;
 }
 
 int alloc_batch(hm_context *ctx, hm_batch *b) {
     const size_t bytes = std::max<size_t>(b->n * b->value_words * 8, 16);
     // Stream-ordered pool for ordinary batches (no device-wide sync, blocks are recycled).  Multi-GB results go through
     // plain cudaMalloc: returning such a block to the pool costs ~0.5 s of unmapping at the next synchronisation.
+    cudaError_t e;
     if (bytes <= ((size_t)1 << 30)) {
-        CK(cudaMallocAsync(&b->d, bytes, ctx->stream));
+        e = pool_alloc(ctx, &b->d, bytes);
         b->pooled = true;
     } else {
-        CK(cudaMalloc(&b->d, bytes));
+        e = cudaMalloc(&b->d, bytes);
         b->pooled = false;
+    }
+    if (e != cudaSuccess) {
+        b->d = nullptr;
+        fail_cuda(ctx, e, "batch allocation");
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? HM_ERR_OUT_OF_MEMORY : HM_ERR_CUDA;
     }
     return HM_OK;
 }
@@ -328,8 +406,9 @@ int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *
             if (!no_thread && (uint64_t)n * xchunks_sum >= (g_mul_thread_min >= 0 ? (uint64_t)g_mul_thread_min : (uint64_t)ctx->sm_count * 128) &&
                 (uint64_t)n * cnt * xchunks_max <= ((uint64_t)1 << 22) && cnt <= 65535 && xchunks_max <= 65535) {
                 const size_t threads = (size_t)((n + 127) / 128) * 128 * cnt * xchunks_max;
-                uint32_t *scratch = nullptr;
-                CK(cudaMallocAsync(&scratch, threads * hmk::ADT_THREAD_WORDS * 4, ctx->stream));
+                PoolGuard scratch_guard(ctx);
+                CK(pool_alloc(ctx, &scratch_guard.p, threads * hmk::ADT_THREAD_WORDS * 4));
+                uint32_t *scratch = static_cast<uint32_t *>(scratch_guard.p);
                 // outputs are accumulated with atomics: zero them first (unless the caller already did)
                 for (size_t i = 0; i < cnt && !outputs_zeroed; ++i) {
                     const MulOp &o = h_ops[i];
@@ -343,7 +422,6 @@ int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *
                 const dim3 grid_t3((unsigned)((n + 127) / 128), (unsigned)cnt, (unsigned)xchunks_max);
                 if (chunk32) hmk::mul_thread32_kernel<<<grid_t3, 128, 0, ctx->stream>>>(d_ops, n, scratch);
                 else hmk::mul_thread_kernel<<<grid_t3, 128, 0, ctx->stream>>>(d_ops, n, scratch);
-                cudaFreeAsync(scratch, ctx->stream);
                 break;
             }
             const dim3 grid_w((unsigned)((n + 3) / 4), (unsigned)cnt);
@@ -537,6 +615,7 @@ const char *hm_status_string(int s) {
         case HM_ERR_UNSUPPORTED: return "shape not supported by the kernels";
         case HM_ERR_INVALID_ARGUMENT: return "invalid argument";
         case HM_ERR_DIVIDE_BY_ZERO: return "attempt to divide by zero";
+        case HM_ERR_OUT_OF_MEMORY: return "out of host or device memory";
         default: return "unknown status";
     }
 }
@@ -576,11 +655,20 @@ int hm_context_create(uint16_t d, uint16_t dp, uint16_t delta, uint16_t tau, int
         delete ctx;
         return HM_ERR_CUDA;
     }
-    {   // keep freed blocks in the stream-ordered pool instead of returning them to the driver at every sync
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+    {   // a private stream-ordered pool that keeps freed blocks (no trimming at every synchronisation); the device's default
+        // pool, which the rest of the process may be using, is left alone
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess && ctx->pool) {
             uint64_t keep = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            ctx->pool = nullptr; // fall back to the default pool, untouched
+            cudaGetLastError();
         }
     }
     cudaDeviceProp prop;
@@ -596,10 +684,23 @@ void hm_context_destroy(hm_context *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    // Batches the caller still holds lose their device memory here and become orphans: hm_batch_free(NULL or any ctx, b)
+    // on an orphan only releases the host-side handle, so the two destruction orders are both safe.
+    for (hm_batch *b : ctx->live) {
+        if (b->d) {
+            if (b->pooled) cudaFreeAsync(b->d, ctx->stream);
+            else cudaFree(b->d);
+        }
+        b->d = nullptr;
+        b->ctx = nullptr;
+    }
+    ctx->live.clear();
+    cudaStreamSynchronize(ctx->stream);
     clear_secret(ctx);
     clear_public(ctx);
     if (ctx->d_ops) cudaFree(ctx->d_ops);
     if (ctx->h_ops) cudaFreeHost(ctx->h_ops);
+    if (ctx->d_sched) cudaFree(ctx->d_sched);
     if (ctx->side_stream) {
         cudaStreamSynchronize(ctx->side_stream);
         cudaStreamDestroy(ctx->side_stream);
@@ -607,6 +708,7 @@ void hm_context_destroy(hm_context *ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     delete ctx;
 }
 
@@ -647,6 +749,21 @@ int hm_set_tuning(const char *key, long value) {
     if (!key) return HM_ERR_INVALID_ARGUMENT;
     if (strcmp(key, "adder_thread_min") == 0) {
         g_adder_thread_min = value;
+        return HM_OK;
+    }
+    if (strcmp(key, "adder_chain") == 0) {
+        if (value != 0 && value != 3 && value != 4 && value != 12 && value != 13) return HM_ERR_INVALID_ARGUMENT;
+        g_adder_chain = value;
+        return HM_OK;
+    }
+    if (strcmp(key, "adder_phases") == 0) {
+        if (value < 1 || value > (long)hmk::ADDER_MAX_PHASES) return HM_ERR_INVALID_ARGUMENT;
+        g_adder_phases = value;
+        return HM_OK;
+    }
+    if (strcmp(key, "host_chunk_mb") == 0) {
+        if (value < 1 || value > 4096) return HM_ERR_INVALID_ARGUMENT;
+        g_host_chunk_mb = value;
         return HM_OK;
     }
     if (strcmp(key, "mul_thread_min") == 0) {
@@ -796,15 +913,21 @@ void *hm_batch_device_ptr(const hm_batch *b) { return b ? (void *)b->d : nullptr
 
 void hm_batch_free(hm_context *ctx, hm_batch *b) {
     if (!b) return;
-    if (!ctx) ctx = b->ctx;
-    if (ctx) cudaSetDevice(ctx->device);
-    if (b->d) {
-        if (ctx && b->pooled) {
-            cudaFreeAsync(b->d, ctx->stream); // ordered after every kernel of this context that used it
-        } else {
-            if (ctx) cudaStreamSynchronize(ctx->stream);
-            cudaFree(b->d);
+    // The owning context is the one recorded in the batch; it is NULL once that context has been destroyed (the batch is
+    // then an orphan without device memory).  The `ctx` argument is accepted for symmetry with the other calls only.
+    (void)ctx;
+    hm_context *owner = b->ctx;
+    if (owner) {
+        cudaSetDevice(owner->device);
+        if (b->d) {
+            if (b->pooled) {
+                cudaFreeAsync(b->d, owner->stream); // ordered after every kernel of this context that used it
+            } else {
+                cudaStreamSynchronize(owner->stream);
+                cudaFree(b->d);
+            }
         }
+        owner->live.erase(b);
     }
     delete b;
 }
@@ -814,11 +937,12 @@ int hm_batch_upload_bounded(hm_context *ctx, size_t n, uint32_t L, const uint64_
     if (!ctx || !out || !degree_bounds || (!host && n) || L == 0 || L > (uint32_t)hmk::MAX_SLOTS)
         return HM_ERR_INVALID_ARGUMENT;
     USE_DEV(ctx);
-    hm_batch *b = new_batch(ctx, n, L, degree_bounds);
-    if (!b) return HM_ERR_INVALID_ARGUMENT;
+    int nb_status = HM_OK;
+    hm_batch *b = new_batch(ctx, n, L, degree_bounds, &nb_status);
+    if (!b) return nb_status;
     int rc = alloc_batch(ctx, b);
     if (rc != HM_OK) {
-        delete b;
+        discard_batch(b);
         return rc;
     }
     if (n) {
@@ -855,14 +979,21 @@ int hm_batch_download(hm_context *ctx, const hm_batch *b, uint64_t *host) {
 int hm_batch_clone(hm_context *ctx, const hm_batch *b, hm_batch **out) {
     if (!ctx || !b || !out) return HM_ERR_INVALID_ARGUMENT;
     USE_DEV(ctx);
-    hm_batch *c = new_batch(ctx, b->n, b->L, b->degb.data());
-    if (!c) return HM_ERR_INVALID_ARGUMENT;
+    int nb_status = HM_OK;
+    hm_batch *c = new_batch(ctx, b->n, b->L, b->degb.data(), &nb_status);
+    if (!c) return nb_status;
     int rc = alloc_batch(ctx, c);
     if (rc != HM_OK) {
-        delete c;
+        discard_batch(c);
         return rc;
     }
-    if (b->n) CK(cudaMemcpyAsync(c->d, b->d, b->n * b->value_words * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (b->n) {
+        cudaError_t e = cudaMemcpyAsync(c->d, b->d, b->n * b->value_words * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            hm_batch_free(ctx, c);
+            return fail_cuda(ctx, e, "clone");
+        }
+    }
     *out = c;
     return HM_OK;
 }
@@ -913,40 +1044,58 @@ int hm_batch_serialize(hm_context *ctx, const hm_batch *b, uint8_t *out, size_t 
     return HM_OK;
 }
 
-int hm_batch_deserialize(hm_context *ctx, const uint8_t *in, size_t len, hm_batch **out) {
-    if (!ctx || !in || !out) return HM_ERR_INVALID_ARGUMENT;
+// Validates a wire header against its own length without trusting any field: checked arithmetic only.  The parser sees
+// ciphertexts produced by other parties.
+int hm_batch_wire_inspect(const uint8_t *in, size_t len, uint16_t params_out[4], uint32_t *L_out, uint64_t *n_out,
+                          uint64_t *value_words_out) {
+    if (!in) return HM_ERR_INVALID_ARGUMENT;
     if (len < WIRE_HEADER_BYTES || memcmp(in, "HMB1", 4) != 0) return HM_ERR_INVALID_ARGUMENT;
     const uint8_t *p = in + 4;
-    uint16_t d, dp, delta, tau;
+    uint16_t prm[4];
     uint32_t L;
     uint64_t n;
-    get(p, &d, 2);
-    get(p, &dp, 2);
-    get(p, &delta, 2);
-    get(p, &tau, 2);
+    get(p, prm, 8);
     get(p, &L, 4);
     get(p, &n, 8);
-    if (d != ctx->d || dp != ctx->dp || delta != ctx->delta || tau != ctx->tau) return HM_ERR_INVALID_PARAMETERS;
-    if (L == 0 || L > (uint32_t)hmk::MAX_SLOTS || len < WIRE_HEADER_BYTES + (size_t)L * 8) return HM_ERR_INVALID_ARGUMENT;
+    if (L == 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
+    if (len - WIRE_HEADER_BYTES < (size_t)L * 8) return HM_ERR_INVALID_LENGTH;
     std::vector<uint64_t> degb(L);
     get(p, degb.data(), (size_t)L * 8);
-    size_t vw = 0;
-    for (uint32_t k = 0; k < L; ++k) {
-        if (degb[k] > ((uint64_t)1 << 40)) return HM_ERR_INVALID_ARGUMENT;
-        vw += degb[k] / 64 + 1;
-    }
-    if (len != WIRE_HEADER_BYTES + (size_t)L * 8 + n * vw * 8) return HM_ERR_INVALID_LENGTH;
+    const uint64_t vw = checked_value_words(L, degb.data()); // every bound <= 2^31, sum of widths < 2^32
+    if (vw == 0) return HM_ERR_INVALID_ARGUMENT;
+    const size_t body = len - WIRE_HEADER_BYTES - (size_t)L * 8;
+    // body must be exactly n * vw * 8 bytes: compare by division, never by a product that could wrap
+    if (body % (vw * 8) != 0 || (uint64_t)(body / (vw * 8)) != n) return HM_ERR_INVALID_LENGTH;
+    if (params_out) memcpy(params_out, prm, 8);
+    if (L_out) *L_out = L;
+    if (n_out) *n_out = n;
+    if (value_words_out) *value_words_out = vw;
+    return HM_OK;
+}
+
+int hm_batch_deserialize(hm_context *ctx, const uint8_t *in, size_t len, hm_batch **out) {
+    if (!ctx || !in || !out) return HM_ERR_INVALID_ARGUMENT;
+    uint16_t prm[4];
+    uint32_t L = 0;
+    uint64_t n = 0, vw = 0;
+    int rc = hm_batch_wire_inspect(in, len, prm, &L, &n, &vw);
+    if (rc != HM_OK) return rc;
+    if (prm[0] != ctx->d || prm[1] != ctx->dp || prm[2] != ctx->delta || prm[3] != ctx->tau) return HM_ERR_INVALID_PARAMETERS;
+    std::vector<uint64_t> degb(L);
+    memcpy(degb.data(), in + WIRE_HEADER_BYTES, (size_t)L * 8);
+    const uint8_t *p = in + WIRE_HEADER_BYTES + (size_t)L * 8;
     // the body may be unaligned inside the caller's buffer: upload byte-wise
     USE_DEV(ctx);
-    hm_batch *b = new_batch(ctx, n, L, degb.data());
-    if (!b) return HM_ERR_INVALID_ARGUMENT;
-    int rc = alloc_batch(ctx, b);
+    int nb_status = HM_OK;
+    hm_batch *b = new_batch(ctx, (size_t)n, L, degb.data(), &nb_status);
+    if (!b) return nb_status;
+    rc = alloc_batch(ctx, b);
     if (rc != HM_OK) {
-        delete b;
+        discard_batch(b);
         return rc;
     }
     if (n) {
-        cudaError_t e = cudaMemcpyAsync(b->d, p, n * vw * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(b->d, p, (size_t)n * vw * 8, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             hm_batch_free(ctx, b);
@@ -983,6 +1132,69 @@ int hm_batch_download_canonical(hm_context *ctx, const hm_batch *b, uint64_t *ou
     return HM_OK;
 }
 
+// Inverse of hm_batch_download_canonical: per polynomial (value-major, slot-minor) `u64 degree` then degree/64+1 words,
+// as a Rust build of the reference would export its Polynomial { coefficients, degree } (src/polynomial.rs:22-26).  The
+// engine's slot k gets the width of the largest degree seen in slot k (or of degree_bounds[k] when given, which must then
+// cover every polynomial of the slot).  Rejects a stated degree that disagrees with the words (src/polynomial.rs:35-42).
+int hm_batch_upload_canonical(hm_context *ctx, size_t n, uint32_t L, const uint64_t *in, size_t in_words, const uint64_t *degree_bounds,
+                              hm_batch **out) {
+    if (!ctx || !out || (!in && n) || L == 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    std::vector<uint64_t> degb(L, 0);
+    // pass 1: validate and find the slot bounds
+    size_t pos = 0;
+    for (size_t v = 0; v < n; ++v)
+        for (uint32_t k = 0; k < L; ++k) {
+            if (pos >= in_words) return HM_ERR_INVALID_LENGTH;
+            const uint64_t deg = in[pos];
+            if (deg > MAX_DEGREE_BOUND) return HM_ERR_INVALID_ARGUMENT;
+            const size_t nw = (size_t)(deg / 64 + 1);
+            if (in_words - pos - 1 < nw) return HM_ERR_INVALID_LENGTH;
+            if (gf2::degree(in + pos + 1, nw) != deg) return HM_ERR_INVALID_ARGUMENT;
+            degb[k] = std::max(degb[k], deg);
+            pos += 1 + nw;
+        }
+    if (pos != in_words) return HM_ERR_INVALID_LENGTH;
+    if (degree_bounds)
+        for (uint32_t k = 0; k < L; ++k) {
+            if (degree_bounds[k] < degb[k]) return HM_ERR_INVALID_ARGUMENT;
+            degb[k] = degree_bounds[k];
+        }
+    int nb_status = HM_OK;
+    hm_batch *b = new_batch(ctx, n, L, degb.data(), &nb_status);
+    if (!b) return nb_status;
+    int rc = alloc_batch(ctx, b);
+    if (rc != HM_OK) {
+        discard_batch(b);
+        return rc;
+    }
+    // pass 2: zero-padded slots
+    std::vector<uint64_t> host;
+    try {
+        host.assign(n * b->value_words, 0);
+    } catch (const std::bad_alloc &) {
+        hm_batch_free(ctx, b);
+        return HM_ERR_OUT_OF_MEMORY;
+    }
+    pos = 0;
+    for (size_t v = 0; v < n; ++v)
+        for (uint32_t k = 0; k < L; ++k) {
+            const size_t nw = (size_t)(in[pos] / 64 + 1);
+            memcpy(&host[v * b->value_words + b->off[k]], in + pos + 1, nw * 8);
+            pos += 1 + nw;
+        }
+    if (n) {
+        cudaError_t e = cudaMemcpyAsync(b->d, host.data(), host.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            hm_batch_free(ctx, b);
+            return fail_cuda(ctx, e, "upload canonical");
+        }
+    }
+    *out = b;
+    return HM_OK;
+}
+
 void *hm_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -1005,8 +1217,9 @@ int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32
     if (L == 0 || L % 8 != 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
     USE_DEV(ctx);
     std::vector<uint64_t> degb(L, ctx->fresh_deg);
-    hm_batch *b = new_batch(ctx, n, L, degb.data());
-    if (!b) return HM_ERR_INVALID_ARGUMENT;
+    int nb_status = HM_OK;
+    hm_batch *b = new_batch(ctx, n, L, degb.data(), &nb_status);
+    if (!b) return nb_status;
     int rc = alloc_batch(ctx, b);
     if (rc == HM_OK) rc = encrypt_exec(ctx, d_values, n, L, d_masks, b);
     if (rc != HM_OK) {
@@ -1095,8 +1308,8 @@ int hm_encrypt(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, con
     USE_DEV(ctx);
     const size_t vbytes = n * (L / 8), mbytes = n * L * ((ctx->tau + 7u) / 8u);
     uint8_t *dv = nullptr, *dm = nullptr;
-    CK(cudaMallocAsync(&dv, std::max<size_t>(vbytes, 16), ctx->stream));
-    cudaError_t e = cudaMallocAsync(&dm, std::max<size_t>(mbytes, 16), ctx->stream);
+    CK(pool_alloc(ctx, &dv, std::max<size_t>(vbytes, 16)));
+    cudaError_t e = pool_alloc(ctx, &dm, std::max<size_t>(mbytes, 16));
     if (e != cudaSuccess) {
         cudaFreeAsync(dv, ctx->stream);
         return fail_cuda(ctx, e, "cudaMalloc(masks)");
@@ -1146,8 +1359,8 @@ int hm_encrypt_seeded(hm_context *ctx, const uint8_t *values, size_t n, uint32_t
     USE_DEV(ctx);
     const size_t vbytes = n * (L / 8), mbytes = n * L * ((ctx->tau + 7u) / 8u);
     uint8_t *dv = nullptr, *dm = nullptr;
-    CK(cudaMallocAsync(&dv, std::max<size_t>(vbytes, 16), ctx->stream));
-    cudaError_t e = cudaMallocAsync(&dm, std::max<size_t>(mbytes, 16), ctx->stream);
+    CK(pool_alloc(ctx, &dv, std::max<size_t>(vbytes, 16)));
+    cudaError_t e = pool_alloc(ctx, &dm, std::max<size_t>(mbytes, 16));
     if (e != cudaSuccess) {
         cudaFreeAsync(dv, ctx->stream);
         return fail_cuda(ctx, e, "cudaMalloc(masks)");
@@ -1229,7 +1442,7 @@ int hm_decrypt(hm_context *ctx, const hm_batch *b, uint8_t *values_out) {
     USE_DEV(ctx);
     const size_t bytes = b->n * (b->L / 8);
     uint8_t *dout = nullptr;
-    CK(cudaMallocAsync(&dout, std::max<size_t>(bytes, 16), ctx->stream));
+    CK(pool_alloc(ctx, &dout, std::max<size_t>(bytes, 16)));
     int rc = hm_decrypt_device(ctx, b, dout);
     if (rc == HM_OK && bytes) {
         cudaError_t e = cudaMemcpyAsync(values_out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1326,14 +1539,25 @@ static int result_bounds(int op, uint32_t L, const uint64_t *da, const uint64_t 
     }
 }
 
+int hm_result_slot_bounds(int op, uint32_t L, const uint64_t *a_bounds, const uint64_t *b_bounds, uint64_t *out_bounds) {
+    if (!a_bounds || !b_bounds || !out_bounds || L == 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
+    for (uint32_t k = 0; k < L; ++k)
+        if (a_bounds[k] > MAX_DEGREE_BOUND || b_bounds[k] > MAX_DEGREE_BOUND) return HM_ERR_INVALID_ARGUMENT;
+    std::vector<uint64_t> o;
+    int rc = result_bounds(op, L, a_bounds, b_bounds, o);
+    if (rc != HM_OK) return rc;
+    for (uint32_t k = 0; k < L; ++k) out_bounds[k] = o[k];
+    return HM_OK;
+}
+
 int hm_result_slot_words(const hm_context *ctx, int op, uint32_t L, const uint32_t *a_words, const uint32_t *b_words,
                          uint32_t *out_words) {
     if (!ctx || !a_words || !b_words || !out_words || L == 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
     std::vector<uint64_t> da(L), db(L), o;
-    for (uint32_t k = 0; k < L; ++k) {
-        // a width of exactly fresh size is taken as a fresh ciphertext (degree <= fresh_deg)
-        da[k] = (ctx->has_pk && a_words[k] == ctx->wf) ? ctx->fresh_deg : (uint64_t)a_words[k] * 64 - 1;
-        db[k] = (ctx->has_pk && b_words[k] == ctx->wf) ? ctx->fresh_deg : (uint64_t)b_words[k] * 64 - 1;
+    for (uint32_t k = 0; k < L; ++k) { // a width says nothing about the degree inside: widest case, like hm_batch_upload
+        if (!a_words[k] || !b_words[k]) return HM_ERR_INVALID_ARGUMENT;
+        da[k] = (uint64_t)a_words[k] * 64 - 1;
+        db[k] = (uint64_t)b_words[k] * 64 - 1;
     }
     int rc = result_bounds(op, L, da.data(), db.data(), o);
     if (rc != HM_OK) return rc;
@@ -1352,9 +1576,10 @@ static int add_generic_seq(hm_context *ctx, const hm_batch *a, const hm_batch *b
     for (uint32_t k = 0; k < L; ++k) dgmax = std::max(dgmax, a->degb[k] + b->degb[k]);
     const uint32_t wmax = (uint32_t)((maxdeg + dgmax) / 64 + 2);
     const uint32_t NBUF = 7;
-    uint64_t *arena = nullptr;
+    PoolGuard arena_guard(ctx); // released in stream order on every exit path
     const size_t arena_words = (size_t)NBUF * wmax;
-    CK(cudaMallocAsync(&arena, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
+    CK(pool_alloc(ctx, &arena_guard.p, std::max<size_t>(n * arena_words * 8, 16)));
+    uint64_t *arena = static_cast<uint64_t *>(arena_guard.p);
     CK(cudaMemsetAsync(arena, 0, n * arena_words * 8, ctx->stream));
     auto buf = [&](uint32_t i, uint64_t degb) {
         View v;
@@ -1418,7 +1643,6 @@ static int add_generic_seq(hm_context *ctx, const hm_batch *a, const hm_batch *b
         cur = nxt;
         dc = dt;
     }
-    cudaFreeAsync(arena, ctx->stream);
     return rc;
 }
 
@@ -1462,8 +1686,9 @@ static int add_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
     }
     const size_t arena_words = cursor;
     if (arena_words >> 32) return HM_ERR_UNSUPPORTED;
-    uint64_t *arena = nullptr;
-    CK(cudaMallocAsync(&arena, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
+    PoolGuard arena_guard(ctx); // released in stream order on every exit path
+    CK(pool_alloc(ctx, &arena_guard.p, std::max<size_t>(n * arena_words * 8, 16)));
+    uint64_t *arena = static_cast<uint64_t *>(arena_guard.p);
     // products may be accumulated with atomics (thread-per-chunk kernel): clear their destinations once
     CK(cudaMemsetAsync(arena, 0, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
     CK(cudaMemsetAsync(o->d, 0, std::max<size_t>(n * o->value_words * 8, 16), ctx->stream));
@@ -1533,7 +1758,6 @@ static int add_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
         }
         rc = launch_xor_ops(ctx, ops, n);
     }
-    cudaFreeAsync(arena, ctx->stream);
     return rc;
 }
 
@@ -1621,8 +1845,9 @@ static int mul_generic_seq(hm_context *ctx, const hm_batch *a, const hm_batch *b
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     if ((double)n * arena_words * 8.0 > 0.9 * (double)free_b) return HM_ERR_UNSUPPORTED;
-    uint64_t *arena = nullptr;
-    CK(cudaMallocAsync(&arena, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
+    PoolGuard arena_guard(ctx); // released in stream order on every exit path
+    CK(pool_alloc(ctx, &arena_guard.p, std::max<size_t>(n * arena_words * 8, 16)));
+    uint64_t *arena = static_cast<uint64_t *>(arena_guard.p);
     CK(cudaMemsetAsync(o->d, 0, n * o->value_words * 8, ctx->stream));
     auto aview = [&](const Obj &ob) {
         View v;
@@ -1669,7 +1894,6 @@ static int mul_generic_seq(hm_context *ctx, const hm_batch *a, const hm_batch *b
             rc = launch_xor_views(ctx, rr, rr, x, n);
         }
     }
-    cudaFreeAsync(arena, ctx->stream);
     return rc;
 }
 
@@ -1725,8 +1949,9 @@ static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     if ((double)n * arena_words * 8.0 > 0.9 * (double)free_b) return HM_ERR_UNSUPPORTED;
-    uint64_t *arena = nullptr;
-    CK(cudaMallocAsync(&arena, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
+    PoolGuard arena_guard(ctx); // released in stream order on every exit path
+    CK(pool_alloc(ctx, &arena_guard.p, std::max<size_t>(n * arena_words * 8, 16)));
+    uint64_t *arena = static_cast<uint64_t *>(arena_guard.p);
     // carries are accumulated with atomics by the thread-per-chunk kernel: clear the arena once instead of per product
     CK(cudaMemsetAsync(arena, 0, std::max<size_t>(n * arena_words * 8, 16), ctx->stream));
     (void)pp_words;
@@ -1793,7 +2018,6 @@ static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
             }
         }
     }
-    cudaFreeAsync(arena, ctx->stream);
     return rc;
 }
 
@@ -1866,7 +2090,31 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                 static const int mode = getenv("HM_ADDER_MODE") ? atoi(getenv("HM_ADDER_MODE")) : 5;
                 // the thread-per-value kernel needs tens of thousands of values to fill the GPU (one value per thread);
                 // smaller batches (and the chunks of the host pipeline) use the warp-per-value kernel
-                if (mode >= 3 && wd == 8 && n >= (g_adder_thread_min >= 0 ? (size_t)g_adder_thread_min : (size_t)ctx->sm_count * 96)) { // thread-per-value Karatsuba chain; mode - 1 = CTAs per SM (cross-over measured: tools/adder_crossover.py)
+                // HM_ADDER_CHAIN: 0 = the round-1 thread kernels below; otherwise the dynamically scheduled chain of kernels_adder.cu,
+                // value = 10 * (window in shared memory) + CTAs per SM.  HM_ADDER_PHASES = work units per value (default 4).
+                const int chain = (int)g_adder_chain, phases = (int)g_adder_phases;
+                const bool big = n >= (g_adder_thread_min >= 0 ? (size_t)g_adder_thread_min : (size_t)ctx->sm_count * 96);
+                if (mode >= 3 && chain && big) {
+                    const size_t words = hmk::adder_chain_sched_words(n);
+                    if (ctx->sched_words < words) {
+                        CK(cudaStreamSynchronize(ctx->stream));
+                        if (ctx->d_sched) cudaFree(ctx->d_sched);
+                        ctx->d_sched = nullptr;
+                        ctx->sched_words = 0;
+                        CK(cudaMalloc(&ctx->d_sched, words * 4));
+                        ctx->sched_words = words;
+                    }
+                    CK(cudaMemsetAsync(ctx->d_sched, 0, words * 4, ctx->stream));
+                    hmk::AdderSched sc;
+                    sc.counter = ctx->d_sched;
+                    sc.done = ctx->d_sched + 1;
+                    sc.ngroups = (uint32_t)((n + 31) / 32);
+                    hmk::adder_chain_plan(a->L, wd, (uint32_t)std::max(1, phases), &sc);
+                    CK(hmk::launch_adder_chain(wd, chain, a->d, b->d, o->d, n, a->L, make_layout(o), sc, ctx->sm_count, ctx->stream));
+                    rc = post_launch(ctx, "adder_chain_kernel");
+                    break;
+                }
+                if (mode >= 3 && wd == 8 && big) { // round-1 thread-per-value kernels; mode - 1 = CTAs per SM (cross-over measured: tools/adder_crossover.py)
                     const int per_sm = (mode - 1 == 3) ? 3 : 4; // 128-thread CTAs per SM (168 or 128 registers per thread)
                     const int blocks = (int)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->sm_count * per_sm);
                     static const int use_smem = getenv("HM_ADDER_SMEM") ? atoi(getenv("HM_ADDER_SMEM")) : 1; // 0 = first thread kernel (scratch in global memory)
@@ -1878,12 +2126,12 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                         rc = post_launch(ctx, "adder_thread_smem_kernel");
                         break;
                     }
-                    uint32_t *scratch = nullptr;
-                    CK(cudaMallocAsync(&scratch, (size_t)blocks * 128 * hmk::ADT_THREAD_WORDS * 4, ctx->stream));
+                    PoolGuard scratch_guard(ctx);
+                    CK(pool_alloc(ctx, &scratch_guard.p, (size_t)blocks * 128 * hmk::ADT_THREAD_WORDS * 4));
+                    uint32_t *scratch = static_cast<uint32_t *>(scratch_guard.p);
                     auto tk = hmk::adder_thread_kernel<4>; // the first thread kernel (scratch in global memory), HM_ADDER_SMEM=0
                     tk<<<blocks, 128, 0, ctx->stream>>>(a->d, b->d, o->d, n, a->L, make_layout(o), scratch);
                     rc = post_launch(ctx, "adder_thread_kernel");
-                    cudaFreeAsync(scratch, ctx->stream);
                     break;
                 }
                 auto kern = wd == 4 ? hmk::adder_fused_kernel<4, 1, 0>
@@ -1912,11 +2160,12 @@ static int apply2_impl(hm_context *ctx, int op, const hm_batch *a, const hm_batc
     std::vector<uint64_t> bounds;
     int rc = result_bounds(op, a->L, a->degb.data(), b->degb.data(), bounds);
     if (rc != HM_OK) return rc;
-    hm_batch *o = new_batch(ctx, a->n, a->L, bounds.data());
-    if (!o) return HM_ERR_INVALID_ARGUMENT;
+    int nb_status = HM_OK;
+    hm_batch *o = new_batch(ctx, a->n, a->L, bounds.data(), &nb_status);
+    if (!o) return nb_status;
     rc = alloc_batch(ctx, o);
     if (rc != HM_OK) {
-        delete o;
+        discard_batch(o);
         return rc;
     }
     rc = apply2_exec(ctx, op, a, b, o, force_generic);
@@ -1959,11 +2208,12 @@ int hm_batch_slice(hm_context *ctx, const hm_batch *src, uint32_t first_bit, uin
     if (!ctx || !src || !out || n_bits == 0) return HM_ERR_INVALID_ARGUMENT;
     if ((uint64_t)first_bit + n_bits > src->L) return HM_ERR_INVALID_LENGTH; // split_at past the end panics in the reference
     USE_DEV(ctx);
-    hm_batch *o = new_batch(ctx, src->n, n_bits, src->degb.data() + first_bit);
-    if (!o) return HM_ERR_INVALID_ARGUMENT;
+    int nb_status = HM_OK;
+    hm_batch *o = new_batch(ctx, src->n, n_bits, src->degb.data() + first_bit, &nb_status);
+    if (!o) return nb_status;
     int rc = alloc_batch(ctx, o);
     if (rc != HM_OK) {
-        delete o;
+        discard_batch(o);
         return rc;
     }
     std::vector<MulOp> ops;
@@ -1986,11 +2236,12 @@ int hm_batch_concat(hm_context *ctx, const hm_batch *const *parts, size_t count,
     }
     if (degb.size() > (size_t)hmk::MAX_SLOTS) return HM_ERR_UNSUPPORTED;
     USE_DEV(ctx);
-    hm_batch *o = new_batch(ctx, parts[0]->n, (uint32_t)degb.size(), degb.data());
-    if (!o) return HM_ERR_INVALID_ARGUMENT;
+    int nb_status = HM_OK;
+    hm_batch *o = new_batch(ctx, parts[0]->n, (uint32_t)degb.size(), degb.data(), &nb_status);
+    if (!o) return nb_status;
     int rc = alloc_batch(ctx, o);
     if (rc != HM_OK) {
-        delete o;
+        discard_batch(o);
         return rc;
     }
     std::vector<MulOp> ops;
@@ -2054,100 +2305,125 @@ int hm_apply1(hm_context *ctx, int op, hm_batch *a) {
     return HM_OK;
 }
 
-int hm_apply2_host(hm_context *ctx, int op, size_t n, uint32_t L, const uint32_t *a_words, const uint64_t *a_host,
-                   const uint32_t *b_words, const uint64_t *b_host, uint64_t *out_host) {
-    if (!ctx || !a_words || !b_words || (!a_host && n) || (!b_host && n) || (!out_host && n)) return HM_ERR_INVALID_ARGUMENT;
-    int rc = validate_operation(ctx, op);
-    if (rc != HM_OK) return rc;
-    if (L == 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
-    USE_DEV(ctx);
-    std::vector<uint64_t> da(L), db(L);
-    size_t vwa = 0, vwb = 0;
-    for (uint32_t k = 0; k < L; ++k) {
-        if (!a_words[k] || !b_words[k]) return HM_ERR_INVALID_ARGUMENT;
-        da[k] = (ctx->has_pk && a_words[k] == ctx->wf) ? ctx->fresh_deg : (uint64_t)a_words[k] * 64 - 1;
-        db[k] = (ctx->has_pk && b_words[k] == ctx->wf) ? ctx->fresh_deg : (uint64_t)b_words[k] * 64 - 1;
-        vwa += a_words[k];
-        vwb += b_words[k];
-    }
-    std::vector<uint64_t> bo;
-    rc = result_bounds(op, L, da.data(), db.data(), bo);
-    if (rc != HM_OK) return rc;
-    size_t vwo = 0;
-    for (uint32_t k = 0; k < L; ++k) vwo += bo[k] / 64 + 1;
-    // chunked pipeline on three streams: upload of chunk c+1 and download of chunk c-1 overlap the
-    // kernels of chunk c.  Two stages of device buffers are allocated once and reused.
-    const size_t per_value_bytes = (vwa + vwb + vwo) * 8;
-    size_t chunk = std::max<size_t>(1, std::min<size_t>(n, ((size_t)96 << 20) / std::max<size_t>(per_value_bytes, 1)));
-    if (chunk > 1024) chunk &= ~(size_t)1023;
-    cudaStream_t user = ctx->stream;
+// Host-buffer pipeline shared by hm_apply2_host / hm_apply2_host_bounded: chunks of values, upload of chunk c+1 and
+// download of chunk c-1 overlap the kernels of chunk c on three streams; two stages of device buffers, allocated once.
+namespace {
+struct HostPipe { // owns the streams, events and stage batches; released on every exit path
+    hm_context *ctx;
     cudaStream_t s_up = nullptr, s_down = nullptr;
-    CK(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&s_down, cudaStreamNonBlocking));
     struct Stage {
         hm_batch *a = nullptr, *b = nullptr, *o = nullptr;
         cudaEvent_t up = nullptr, done = nullptr, down = nullptr;
         bool used = false;
     } st[2];
+    explicit HostPipe(hm_context *c) : ctx(c) {}
+    ~HostPipe() {
+        if (s_up) cudaStreamSynchronize(s_up);
+        cudaStreamSynchronize(ctx->stream);
+        if (s_down) cudaStreamSynchronize(s_down);
+        for (Stage &s : st) {
+            if (s.a) hm_batch_free(ctx, s.a);
+            if (s.b) hm_batch_free(ctx, s.b);
+            if (s.o) hm_batch_free(ctx, s.o);
+            if (s.up) cudaEventDestroy(s.up);
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.down) cudaEventDestroy(s.down);
+        }
+        if (s_up) cudaStreamDestroy(s_up);
+        if (s_down) cudaStreamDestroy(s_down);
+    }
+};
+} // namespace
+
+static int apply2_host_impl(hm_context *ctx, int op, size_t n, uint32_t L, const uint64_t *da, const uint64_t *a_host, const uint64_t *db,
+                            const uint64_t *b_host, uint64_t *out_host) {
+    std::vector<uint64_t> bo;
+    int rc = result_bounds(op, L, da, db, bo);
+    if (rc != HM_OK) return rc;
+    const uint64_t vwa = checked_value_words(L, da), vwb = checked_value_words(L, db), vwo = checked_value_words(L, bo.data());
+    if (!vwa || !vwb || !vwo) return HM_ERR_INVALID_ARGUMENT;
+    if (n == 0) return HM_OK;
+    const size_t per_value_bytes = (size_t)(vwa + vwb + vwo) * 8;
+    const size_t chunk_bytes = (size_t)(g_host_chunk_mb > 0 ? g_host_chunk_mb : 96) << 20;
+    size_t chunk = std::max<size_t>(1, std::min<size_t>(n, chunk_bytes / per_value_bytes));
+    if (chunk > 1024) chunk &= ~(size_t)1023;
+    cudaStream_t user = ctx->stream;
+    HostPipe hp(ctx);
+    CK(cudaStreamCreateWithFlags(&hp.s_up, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&hp.s_down, cudaStreamNonBlocking));
     const int nstages = (n > chunk) ? 2 : 1;
-    for (int i = 0; i < nstages && rc == HM_OK; ++i) {
-        Stage &s = st[i];
-        cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&s.down, cudaEventDisableTiming);
-        s.a = new_batch(ctx, chunk, L, da.data());
-        s.b = new_batch(ctx, chunk, L, db.data());
-        s.o = new_batch(ctx, chunk, L, bo.data());
-        if (!s.a || !s.b || !s.o) rc = HM_ERR_INVALID_ARGUMENT;
-        if (rc == HM_OK) rc = alloc_batch(ctx, s.a);
-        if (rc == HM_OK) rc = alloc_batch(ctx, s.b);
-        if (rc == HM_OK) rc = alloc_batch(ctx, s.o);
+    for (int i = 0; i < nstages; ++i) {
+        HostPipe::Stage &s = hp.st[i];
+        CK(cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.down, cudaEventDisableTiming));
+        int st = HM_OK;
+        if (!(s.a = new_batch(ctx, chunk, L, da, &st))) return st;
+        if (!(s.b = new_batch(ctx, chunk, L, db, &st))) return st;
+        if (!(s.o = new_batch(ctx, chunk, L, bo.data(), &st))) return st;
+        if ((rc = alloc_batch(ctx, s.a)) != HM_OK || (rc = alloc_batch(ctx, s.b)) != HM_OK || (rc = alloc_batch(ctx, s.o)) != HM_OK) return rc;
     }
     {   // the stage buffers were allocated in `user` stream order: the copy streams must not touch them earlier
         cudaEvent_t ready = nullptr;
-        cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
-        cudaEventRecord(ready, user);
-        cudaStreamWaitEvent(s_up, ready, 0);
-        cudaStreamWaitEvent(s_down, ready, 0);
+        CK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(ready, user);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.s_up, ready, 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(hp.s_down, ready, 0);
         cudaEventDestroy(ready);
+        CK(e);
     }
     size_t idx = 0;
-    for (size_t first = 0; first < n && rc == HM_OK; first += chunk, ++idx) {
-        Stage &s = st[idx % nstages];
+    for (size_t first = 0; first < n; first += chunk, ++idx) {
+        HostPipe::Stage &s = hp.st[idx % nstages];
         const size_t cnt = std::min(chunk, n - first);
         if (s.used) {
-            cudaStreamWaitEvent(s_up, s.done, 0); // inputs of this stage were consumed
-            cudaStreamWaitEvent(user, s.down, 0); // its previous result has left the device
+            CK(cudaStreamWaitEvent(hp.s_up, s.done, 0)); // inputs of this stage were consumed
+            CK(cudaStreamWaitEvent(user, s.down, 0));    // its previous result has left the device
         }
         s.a->n = s.b->n = s.o->n = cnt;
-        cudaMemcpyAsync(s.a->d, a_host + first * vwa, cnt * vwa * 8, cudaMemcpyHostToDevice, s_up);
-        cudaMemcpyAsync(s.b->d, b_host + first * vwb, cnt * vwb * 8, cudaMemcpyHostToDevice, s_up);
-        cudaEventRecord(s.up, s_up);
-        cudaStreamWaitEvent(user, s.up, 0);
+        CK(cudaMemcpyAsync(s.a->d, a_host + first * vwa, cnt * vwa * 8, cudaMemcpyHostToDevice, hp.s_up));
+        CK(cudaMemcpyAsync(s.b->d, b_host + first * vwb, cnt * vwb * 8, cudaMemcpyHostToDevice, hp.s_up));
+        CK(cudaEventRecord(s.up, hp.s_up));
+        CK(cudaStreamWaitEvent(user, s.up, 0));
         rc = apply2_exec(ctx, op, s.a, s.b, s.o, false);
-        if (rc != HM_OK) break;
-        cudaEventRecord(s.done, user);
-        cudaStreamWaitEvent(s_down, s.done, 0);
-        cudaMemcpyAsync(out_host + first * vwo, s.o->d, cnt * vwo * 8, cudaMemcpyDeviceToHost, s_down);
-        cudaEventRecord(s.down, s_down);
+        if (rc != HM_OK) return rc;
+        CK(cudaEventRecord(s.done, user));
+        CK(cudaStreamWaitEvent(hp.s_down, s.done, 0));
+        CK(cudaMemcpyAsync(out_host + first * vwo, s.o->d, cnt * vwo * 8, cudaMemcpyDeviceToHost, hp.s_down));
+        CK(cudaEventRecord(s.down, hp.s_down));
         s.used = true;
     }
-    cudaStreamSynchronize(s_up);
-    cudaStreamSynchronize(user);
-    cudaError_t e = cudaStreamSynchronize(s_down);
-    for (int i = 0; i < nstages; ++i) {
-        Stage &s = st[i];
-        if (s.a) hm_batch_free(ctx, s.a);
-        if (s.b) hm_batch_free(ctx, s.b);
-        if (s.o) hm_batch_free(ctx, s.o);
-        if (s.up) cudaEventDestroy(s.up);
-        if (s.done) cudaEventDestroy(s.done);
-        if (s.down) cudaEventDestroy(s.down);
+    CK(cudaStreamSynchronize(hp.s_up));
+    CK(cudaStreamSynchronize(user));
+    CK(cudaStreamSynchronize(hp.s_down));
+    return HM_OK;
+}
+
+int hm_apply2_host_bounded(hm_context *ctx, int op, size_t n, uint32_t L, const uint64_t *a_bounds, const uint64_t *a_host,
+                           const uint64_t *b_bounds, const uint64_t *b_host, uint64_t *out_host) {
+    if (!ctx || !a_bounds || !b_bounds || (!a_host && n) || (!b_host && n) || (!out_host && n)) return HM_ERR_INVALID_ARGUMENT;
+    int rc = validate_operation(ctx, op);
+    if (rc != HM_OK) return rc;
+    if (L == 0 || L > (uint32_t)hmk::MAX_SLOTS || op == HM_OP_NOT) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    return apply2_host_impl(ctx, op, n, L, a_bounds, a_host, b_bounds, b_host, out_host);
+}
+
+int hm_apply2_host(hm_context *ctx, int op, size_t n, uint32_t L, const uint32_t *a_words, const uint64_t *a_host,
+                   const uint32_t *b_words, const uint64_t *b_host, uint64_t *out_host) {
+    if (!ctx || !a_words || !b_words || (!a_host && n) || (!b_host && n) || (!out_host && n)) return HM_ERR_INVALID_ARGUMENT;
+    int rc = validate_operation(ctx, op);
+    if (rc != HM_OK) return rc;
+    if (L == 0 || L > (uint32_t)hmk::MAX_SLOTS || op == HM_OP_NOT) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    // widths alone say nothing about the degrees inside: every slot is taken at its widest (degree <= 64 w - 1)
+    std::vector<uint64_t> da(L), db(L);
+    for (uint32_t k = 0; k < L; ++k) {
+        if (!a_words[k] || !b_words[k]) return HM_ERR_INVALID_ARGUMENT;
+        da[k] = (uint64_t)a_words[k] * 64 - 1;
+        db[k] = (uint64_t)b_words[k] * 64 - 1;
     }
-    cudaStreamDestroy(s_up);
-    cudaStreamDestroy(s_down);
-    if (rc == HM_OK && e != cudaSuccess) rc = fail_cuda(ctx, e, "apply2_host");
-    return rc;
+    return apply2_host_impl(ctx, op, n, L, da.data(), a_host, db.data(), b_host, out_host);
 }
 
 // ---- raw polynomial batches ----------------------------------------------------------------------
@@ -2163,8 +2439,9 @@ int hm_poly_rem(hm_context *ctx, const hm_batch *a, hm_batch **out) {
     if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;
     USE_DEV(ctx);
     std::vector<uint64_t> bounds(a->L, ctx->ds - 1);
-    hm_batch *o = new_batch(ctx, a->n, a->L, bounds.data());
-    if (!o) return HM_ERR_INVALID_ARGUMENT;
+    int nb_status = HM_OK;
+    hm_batch *o = new_batch(ctx, a->n, a->L, bounds.data(), &nb_status);
+    if (!o) return nb_status;
     int rc = alloc_batch(ctx, o);
     for (uint32_t k = 0; k < a->L && rc == HM_OK; ++k) rc = launch_rem(ctx, slot_view(a, k), slot_view(o, k), a->n);
     if (rc != HM_OK) {
@@ -2241,8 +2518,9 @@ int hm_poly_mulrem(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_bat
     USE_DEV(ctx);
     if (mulrem_fresh_ok(ctx, a, b)) {
         std::vector<uint64_t> bounds(a->L, ctx->ds - 1);
-        hm_batch *o = new_batch(ctx, a->n, a->L, bounds.data());
-        if (!o) return HM_ERR_INVALID_ARGUMENT;
+        int nb_status = HM_OK;
+        hm_batch *o = new_batch(ctx, a->n, a->L, bounds.data(), &nb_status);
+        if (!o) return nb_status;
         int rc = alloc_batch(ctx, o);
         if (rc == HM_OK) rc = mulrem_fresh_exec(ctx, a, b, o);
         if (rc != HM_OK) {

@@ -48,7 +48,8 @@ typedef enum hm_status {
     HM_ERR_CUDA = -6,                /* device missing / CUDA runtime failure                       */
     HM_ERR_UNSUPPORTED = -7,         /* shape outside what the kernels are built for                */
     HM_ERR_INVALID_ARGUMENT = -8,    /* NULL pointer, mismatched batches, empty polynomial          */
-    HM_ERR_DIVIDE_BY_ZERO = -9       /* Polynomial::rem panic              — src/polynomial.rs:319-322 */
+    HM_ERR_DIVIDE_BY_ZERO = -9,      /* Polynomial::rem panic              — src/polynomial.rs:319-322 */
+    HM_ERR_OUT_OF_MEMORY = -10       /* host or device allocation failed (the reference aborts on OOM)   */
 } hm_status;
 
 /* Operation selectors = the marker types of src/impls/numbers.rs:7-25. */
@@ -89,12 +90,17 @@ int hm_context_device(const hm_context *ctx);
  * kernel (-1 = default).  "mul_circuit_sequential": 1 = launch the multiplier circuit's carry products one at a time
  * instead of one batch per column; "adder_generic_sequential": 1 = the generic adder evaluates common.rs:44-53 literally
  * (two long products per bit) instead of the regrouped one-product-per-bit form; "mul_thread_chunk": 24 | 32 words per
- * chunk of the thread-per-chunk product kernel.  All of them give the same polynomials: they are the A/B arms of tests. */
+ * chunk of the thread-per-chunk product kernel; "adder_chain": 0 = the round-1 thread-per-value adder kernels, otherwise
+ * the dynamically scheduled chain of kernels_adder.cu as 10 * (window in shared memory) + CTAs per SM (4 = default, 3, 12, 13);
+ * "adder_phases": work units per value of that chain (1..8); "host_chunk_mb": bytes per stage of the host-buffer pipeline
+ * of hm_apply2_host (MiB, default 96).
+ * All of them give the same polynomials: they are the A/B arms of tests. */
 int hm_set_tuning(const char *key, long value);
 
 /* Context::set_secret_key(SecretKey::from_bytes(bytes)) — src/context.rs:153-155, :568-571.
  * `bytes` is SecretKey::to_bytes(): little-endian u64 words (src/polynomial.rs:99-122).
- * Clears the public key, like the reference.  Degree must equal d. */
+ * Clears the public key, like the reference.  Like the reference, the degree of S is taken from the bytes (it is not
+ * compared with d); the zero polynomial is refused with HM_ERR_DIVIDE_BY_ZERO and S = 1 with HM_ERR_INVALID_ARGUMENT. */
 int hm_set_secret_key(hm_context *ctx, const uint8_t *bytes, size_t len);
 /* Context::set_public_key(PublicKey::from_bytes(..)) — src/context.rs:239-245, :592-595.
  * polys[i]/lens[i] = PublicKey::to_bytes()[i]; n_polys must equal tau. */
@@ -109,6 +115,9 @@ size_t hm_batch_value_words(const hm_batch *b);  /* sum of slot widths, in u64 w
 /* Copies the L slot widths (u64 words) into widths_out[0..L). */
 int hm_batch_slot_words(const hm_batch *b, uint32_t *widths_out);
 void *hm_batch_device_ptr(const hm_batch *b);    /* the padded layout, in HBM                   */
+/* Releases a batch.  The owning context is recorded in the batch, so `ctx` may be NULL.  Batches still alive when their
+ * context is destroyed lose their device memory at that point (they become orphans); freeing an orphan afterwards only
+ * releases the handle, so either destruction order is safe. */
 void hm_batch_free(hm_context *ctx, hm_batch *b);
 /* Host <-> HBM in the padded layout described above (n * value_words u64 words).
  * upload = what a shim does with Vec<CipheredBit> built by Ciphered::new_from_raw
@@ -130,11 +139,22 @@ int hm_batch_slot_degree_bounds(const hm_batch *b, uint64_t *bounds_out);
 size_t hm_batch_serialized_size(const hm_batch *b);
 int hm_batch_serialize(hm_context *ctx, const hm_batch *b, uint8_t *out, size_t capacity);
 int hm_batch_deserialize(hm_context *ctx, const uint8_t *in, size_t len, hm_batch **out);
+/* Header check of a wire buffer without a context or a GPU: every field is validated against `len` with overflow-free
+ * arithmetic (degree bounds <= 2^31, sum of slot widths < 2^32, body length == n * value_words * 8 exactly) — the buffer
+ * may come from another party.  Outputs (each may be NULL): params_out = {d, dp, delta, tau}. */
+int hm_batch_wire_inspect(const uint8_t *in, size_t len, uint16_t params_out[4], uint32_t *L_out, uint64_t *n_out,
+                          uint64_t *value_words_out);
 /* Canonical export for offline comparison with a Rust build of the reference: per polynomial (value-major,
  * slot-minor) `u64 degree` followed by degree/64+1 words — what Polynomial holds (src/polynomial.rs:22-26).
  * out may be NULL to only count; *written = number of u64. */
 int hm_batch_download_canonical(hm_context *ctx, const hm_batch *b, uint64_t *out, size_t capacity_words,
                                 size_t *written);
+/* The inverse: n * L canonical polynomials in the same order and format (e.g. exported by a Rust build of the reference)
+ * become a device batch.  Slot k is as wide as the largest degree seen in slot k, or as degree_bounds[k] when
+ * degree_bounds != NULL (each must cover its slot).  A stated degree that is not the highest set bit of its words is
+ * refused (HM_ERR_INVALID_ARGUMENT); a truncated or over-long buffer gives HM_ERR_INVALID_LENGTH. */
+int hm_batch_upload_canonical(hm_context *ctx, size_t n, uint32_t L, const uint64_t *in, size_t in_words,
+                              const uint64_t *degree_bounds, hm_batch **out);
 /* Page-locked host memory for the host-buffer entry points (hm_encrypt, hm_decrypt, hm_apply2_host,
  * upload/download): pageable memory works too, but is staged by the driver. NULL on failure. */
 void *hm_host_alloc(size_t bytes);
@@ -201,12 +221,21 @@ int hm_apply2_into(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b
 int hm_apply2_generic(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch **out);
 /* MIN_D_OVER_DELTA of an op, or a negative status for an unknown op. */
 int hm_op_min_d_over_delta(int op);
-/* Slot widths (u64 words) of the result of `op` on operands of the given widths; used to size
- * host buffers for hm_apply2_host. */
+/* Degree bounds of the result slots of `op` on operands with the given per-slot degree bounds (the recurrences of
+ * common.rs:37-105 on degrees; slot k is bounds[k]/64+1 words wide).  No context or GPU needed. */
+int hm_result_slot_bounds(int op, uint32_t L, const uint64_t *a_bounds, const uint64_t *b_bounds, uint64_t *out_bounds);
+/* Same from slot widths alone: every operand slot is taken at its widest (degree 64 w - 1), because a width says
+ * nothing about the degrees inside.  Use hm_result_slot_bounds with bounds[k] = d + dp for fresh ciphertexts. */
 int hm_result_slot_words(const hm_context *ctx, int op, uint32_t L, const uint32_t *a_words, const uint32_t *b_words,
                          uint32_t *out_words);
-/* End-to-end convenience = upload a, upload b, apply2, download, with the copies overlapped
- * with compute in chunks of values.  a/b/out are HOST buffers in the padded layout. */
+/* End-to-end convenience = upload a, upload b, apply2, download, with the copies overlapped with compute in chunks of
+ * values (three streams, two stages).  a/b/out are HOST buffers in the padded layout; the result layout is
+ * hm_result_slot_bounds of the operand bounds.  The *_bounded form takes per-slot degree bounds like
+ * hm_batch_upload_bounded — state d + dp for fresh ciphertexts and the fused circuit kernels apply; the plain form
+ * takes widths and assumes the widest degrees (always safe, generic kernels).  Both check every CUDA call and release
+ * their streams, events and stage buffers on every exit path. */
+int hm_apply2_host_bounded(hm_context *ctx, int op, size_t n, uint32_t L, const uint64_t *a_bounds, const uint64_t *a_host,
+                           const uint64_t *b_bounds, const uint64_t *b_host, uint64_t *out_host);
 int hm_apply2_host(hm_context *ctx, int op, size_t n, uint32_t L, const uint32_t *a_words, const uint64_t *a_host,
                    const uint32_t *b_words, const uint64_t *b_host, uint64_t *out_host);
 

@@ -145,3 +145,73 @@ def test_philox_mask_stream_host():
                     row += int(w).to_bytes(4, "little")
             want += row[:mb]
         assert out.tobytes() == bytes(want)
+
+
+def _wire(params, L, n, bounds, body_words=None, magic=b"HMB1"):
+    import struct
+
+    vw = sum(b // 64 + 1 for b in bounds)
+    body = np.zeros(n * vw if body_words is None else body_words, dtype=np.uint64).tobytes()
+    return magic + struct.pack("<4HIQ", *params, L, n) + struct.pack(f"<{len(bounds)}Q", *bounds) + body
+
+
+def test_wire_header_is_validated_without_trusting_it():
+    """hm_batch_wire_inspect (the header check of hm_batch_deserialize) on malformed buffers: crafted sizes must not wrap
+    (n = 2^61 made n * vw * 8 overflow to 0 and the length check pass)."""
+    import struct
+
+    lib = hm.lib()
+    P = (128, 128, 1, 128)
+
+    def inspect(buf):
+        prm = (C.c_uint16 * 4)()
+        L, n, vw = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        rc = lib.hm_batch_wire_inspect(buf, len(buf), prm, C.byref(L), C.byref(n), C.byref(vw))
+        return rc, tuple(prm), L.value, n.value, vw.value
+
+    good = _wire(P, 2, 3, [256, 512])
+    assert inspect(good) == (0, P, 2, 3, 5 + 9)
+    assert inspect(_wire(P, 1, 0, [256]))[0] == 0  # empty batch
+    assert inspect(good[:-8])[0] == N.HM_ERR_INVALID_LENGTH
+    assert inspect(good + b"\0" * 8)[0] == N.HM_ERR_INVALID_LENGTH
+    assert inspect(_wire(P, 2, 3, [256, 512], magic=b"HMB2"))[0] == N.HM_ERR_INVALID_ARGUMENT
+    assert inspect(good[:10])[0] == N.HM_ERR_INVALID_ARGUMENT
+    # n chosen so that n * value_words * 8 wraps to 0 (value_words = 1): 2^61 values and an empty body
+    wrap = b"HMB1" + struct.pack("<4HIQ", *P, 1, 1 << 61) + struct.pack("<Q", 0)
+    assert inspect(wrap)[0] == N.HM_ERR_INVALID_LENGTH
+    wrap2 = b"HMB1" + struct.pack("<4HIQ", *P, 2, (1 << 64) // 16) + struct.pack("<2Q", 0, 0)  # vw = 2: n * 16 = 2^64
+    assert inspect(wrap2)[0] == N.HM_ERR_INVALID_LENGTH
+    # degree bounds beyond what the kernels' 32-bit slot offsets can describe
+    assert inspect(_wire(P, 1, 0, [(1 << 31) + 1], body_words=0))[0] == N.HM_ERR_INVALID_ARGUMENT
+    assert inspect(_wire(P, 1, 0, [1 << 40], body_words=0))[0] == N.HM_ERR_INVALID_ARGUMENT
+    big = [1 << 31] * 128  # each allowed, the sum of widths (128 * 2^25 = 2^32) is not
+    assert inspect(_wire(P, 128, 0, big, body_words=0))[0] == N.HM_ERR_INVALID_ARGUMENT
+    # L = 0, L > 128, truncated bound table
+    assert inspect(b"HMB1" + struct.pack("<4HIQ", *P, 0, 0))[0] == N.HM_ERR_INVALID_ARGUMENT
+    assert inspect(b"HMB1" + struct.pack("<4HIQ", *P, 129, 0) + b"\0" * (129 * 8))[0] == N.HM_ERR_INVALID_ARGUMENT
+    assert inspect(b"HMB1" + struct.pack("<4HIQ", *P, 4, 0) + b"\0" * 8)[0] == N.HM_ERR_INVALID_LENGTH
+    assert lib.hm_batch_wire_inspect(None, 0, None, None, None, None) == N.HM_ERR_INVALID_ARGUMENT
+
+
+def test_result_slot_bounds_follow_the_reference_degrees():
+    """hm_result_slot_bounds = the degree recurrences of common.rs:37-105, no GPU needed."""
+    lib = hm.lib()
+    u64p = C.POINTER(C.c_uint64)
+
+    def bounds(op, da, db):
+        a, b = np.asarray(da, dtype=np.uint64), np.asarray(db, dtype=np.uint64)
+        o = np.zeros(a.size, dtype=np.uint64)
+        rc = lib.hm_result_slot_bounds(op, a.size, a.ctypes.data_as(u64p), b.ctypes.data_as(u64p), o.ctypes.data_as(u64p))
+        return rc, [int(x) for x in o]
+
+    D = 256
+    assert bounds(N.HM_OP_XOR, [D, 100], [7, 300]) == (0, [D, 300])
+    assert bounds(N.HM_OP_AND, [D] * 3, [D] * 3) == (0, [2 * D] * 3)
+    assert bounds(N.HM_OP_OR, [D], [2 * D]) == (0, [3 * D])
+    rc, add = bounds(N.HM_OP_ADD, [D] * 32, [D] * 32)
+    assert rc == 0 and add == [D, 2 * D] + [(3 * k - 1) * D for k in range(2, 32)]  # SURVEY.md A.2
+    rc, mul = bounds(N.HM_OP_MUL, [D] * 8, [D] * 8)
+    assert rc == 0 and [m // D for m in mul] == [2, 2, 4, 6, 10, 18, 32, 56]  # SURVEY.md A.3
+    assert bounds(N.HM_OP_MUL, [D] * 32, [D] * 32)[0] == N.HM_ERR_UNSUPPORTED  # u32 multiplication: infeasible growth
+    assert bounds(N.HM_OP_NOT, [D], [D])[0] == N.HM_ERR_INVALID_ARGUMENT
+    assert bounds(N.HM_OP_ADD, [1 << 40], [1])[0] == N.HM_ERR_INVALID_ARGUMENT

@@ -358,9 +358,10 @@ def test_apply2_host_pipeline(oracle, hm):
     dev = ctx.apply2(hm.HomomorphicAddition, ca, cb)
     wo = dev.slot_words().astype(np.uint32)
     wa = np.full(L, 5, dtype=np.uint32)
-    u32p = C.POINTER(C.c_uint32)
+    fresh = np.full(L, 256, dtype=np.uint64)  # degree bound of a fresh ciphertext: d + dp
+    u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
     out = np.zeros((n, int(wo.sum())), dtype=np.uint64)
-    rc = lib.hm_apply2_host(ctx._h, N.HM_OP_ADD, n, L, wa.ctypes.data_as(u32p), ha.ctypes.data, wa.ctypes.data_as(u32p), hb.ctypes.data, out.ctypes.data)
+    rc = lib.hm_apply2_host_bounded(ctx._h, N.HM_OP_ADD, n, L, fresh.ctypes.data_as(u64p), ha.ctypes.data, fresh.ctypes.data_as(u64p), hb.ctypes.data, out.ctypes.data)
     assert rc == 0
     check = np.concatenate([np.arange(0, 64), np.arange(n - 64, n), rng.integers(0, n, 256)])
     dh = dev.to_host()
@@ -370,14 +371,24 @@ def test_apply2_host_pipeline(oracle, hm):
     want, _ = oracle.apply(oracle.OP_ADD, oracle_encrypt(oracle, pk, a[:k], ma[: k * L * 16]), oracle_encrypt(oracle, pk, b[:k], mb[: k * L * 16]), L,
                            threads=oracle.max_threads())
     np.testing.assert_array_equal(out[:k], expected_padded(want, k, wo))
-    # expected result widths are also what hm_result_slot_words reports
-    rw = np.zeros(L, dtype=np.uint32)
-    assert lib.hm_result_slot_words(ctx._h, N.HM_OP_ADD, L, wa.ctypes.data_as(u32p), wa.ctypes.data_as(u32p), rw.ctypes.data_as(u32p)) == 0
-    np.testing.assert_array_equal(rw, wo)
-    # XOR through the same call (memory-bound op, one chunk)
+    # expected result bounds are also what hm_result_slot_bounds reports
+    rb = np.zeros(L, dtype=np.uint64)
+    assert lib.hm_result_slot_bounds(N.HM_OP_ADD, L, fresh.ctypes.data_as(u64p), fresh.ctypes.data_as(u64p), rb.ctypes.data_as(u64p)) == 0
+    np.testing.assert_array_equal(rb // 64 + 1, wo)
+    np.testing.assert_array_equal(rb, dev.slot_degree_bounds())
+    # XOR through the widths form of the call (memory-bound op, one chunk)
     outx = np.zeros((n, 160), dtype=np.uint64)
     assert lib.hm_apply2_host(ctx._h, N.HM_OP_XOR, n, L, wa.ctypes.data_as(u32p), ha.ctypes.data, wa.ctypes.data_as(u32p), hb.ctypes.data, outx.ctypes.data) == 0
     np.testing.assert_array_equal(outx, ha ^ hb)
+    # The widths form assumes the widest degrees a slot can hold (64 w - 1), so its result layout is wider than the fresh
+    # one; the polynomials are the same.  A few values through the generic kernels:
+    m = 6
+    rw = np.zeros(L, dtype=np.uint32)
+    assert lib.hm_result_slot_words(ctx._h, N.HM_OP_ADD, L, wa.ctypes.data_as(u32p), wa.ctypes.data_as(u32p), rw.ctypes.data_as(u32p)) == 0
+    assert rw[0] == 5 and rw[1] == 10 and np.all(rw >= wo)
+    outw = np.zeros((m, int(rw.sum())), dtype=np.uint64)
+    assert lib.hm_apply2_host(ctx._h, N.HM_OP_ADD, m, L, wa.ctypes.data_as(u32p), ha.ctypes.data, wa.ctypes.data_as(u32p), hb.ctypes.data, outw.ctypes.data) == 0
+    np.testing.assert_array_equal(outw, expected_padded(want, k, rw)[:m])
     # requirement check happens before any work (src/context.rs:310-323)
     ctx2 = hm.Context(hm.Parameters(64, 16, 8, 16))
     assert lib.hm_apply2_host(ctx2._h, N.HM_OP_ADD, 1, 8, wa.ctypes.data_as(u32p), ha.ctypes.data, wa.ctypes.data_as(u32p), hb.ctypes.data, out.ctypes.data) == N.HM_ERR_OPERATION_REQUIREMENT
@@ -668,3 +679,157 @@ def test_add_thread_kernel_small_batches(oracle, hm, dtype, n):
     want, _ = oracle.apply(oracle.OP_ADD, oracle_encrypt(oracle, pk, a[:k], ma[: k * L * 16]), oracle_encrypt(oracle, pk, b[:k], mb[: k * L * 16]), L,
                            threads=oracle.max_threads())
     np.testing.assert_array_equal(r_thread[:k], expected_padded(want, k, r_warp.slot_words()))
+
+
+@pytest.mark.parametrize("params,dtype,n,chain,phases", [
+    (CONFIG_A, np.uint32, 300, 4, 4), (CONFIG_A, np.uint32, 97, 4, 1), (CONFIG_A, np.uint32, 70, 3, 8), (CONFIG_A, np.uint32, 300, 13, 4),
+    (CONFIG_A, np.uint8, 130, 12, 3), (CONFIG_A, np.uint64, 5, 4, 8), (CONFIG_A, np.uint16, 33, 13, 2), (CONFIG_A, np.uint32, 64, 0, 4),
+    ((64, 64, 1, 32), np.uint32, 200, 4, 4), ((64, 64, 1, 32), np.uint8, 45, 13, 2), ((64, 64, 1, 32), np.uint64, 9, 4, 8)])
+def test_add_chain_kernel_variants(oracle, hm, params, dtype, n, chain, phases):
+    """The dynamically scheduled thread-per-value chain (kernels_adder.cu) in every variant the dispatcher can pick — window
+    in registers or shared memory, 2/3/4 CTAs per SM, 1..8 work units per value, D = 256 and D = 128 — forced on small ragged
+    batches: bit-exact against the oracle and against the warp-per-value kernel (common.rs:37-56)."""
+    rng = np.random.default_rng(n * 31 + chain + phases)
+    sk, pk, ctx = setup(oracle, hm, params, 29)
+    tau = params[3]
+    L = np.dtype(dtype).itemsize * 8
+    a = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    b = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    ma, mb = masks_for(rng, n, L, tau), masks_for(rng, n, L, tau)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    lib = hm.lib()
+    try:
+        assert lib.hm_set_tuning(b"adder_thread_min", 0) == 0
+        assert lib.hm_set_tuning(b"adder_chain", chain) == 0
+        assert lib.hm_set_tuning(b"adder_phases", phases) == 0
+        l0 = ctx.kernel_launches()
+        r_chain = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+        assert ctx.kernel_launches() - l0 == 1  # one fused launch
+        got = r_chain.to_host()
+        assert lib.hm_set_tuning(b"adder_thread_min", 1 << 40) == 0
+        r_warp = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+    finally:
+        lib.hm_set_tuning(b"adder_thread_min", -1)
+        lib.hm_set_tuning(b"adder_chain", 4)
+        lib.hm_set_tuning(b"adder_phases", 4)
+    np.testing.assert_array_equal(got, r_warp.to_host())
+    k = min(n, 40)
+    mbytes = (tau + 7) // 8
+    want, _ = oracle.apply(oracle.OP_ADD, oracle_encrypt(oracle, pk, a[:k], ma[: k * L * mbytes]), oracle_encrypt(oracle, pk, b[:k], mb[: k * L * mbytes]), L,
+                           threads=oracle.max_threads())
+    np.testing.assert_array_equal(got[:k], expected_padded(want, k, r_chain.slot_words()))
+    od, _ = oracle.decrypt(sk, want, L)
+    np.testing.assert_array_equal(ctx.decrypt(r_chain)[:k].view(np.uint8), od)
+
+
+def test_into_and_device_entry_points(oracle, hm):
+    """The entry points bench.py times — hm_encrypt_device_into, hm_apply2_into, hm_poly_mulrem_into, hm_decrypt_device —
+    compared word for word with the oracle (they share the kernels of the allocating calls, but are separate ABI paths)."""
+    import ctypes as C
+
+    import torch
+
+    from homomorph_rust_b200 import _native as N
+
+    rng = np.random.default_rng(77)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 41)
+    lib = hm.lib()
+    n, L = 257, 32  # ragged against every tile size
+    a = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    b = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    ma, mb = masks_for(rng, n, L, 128), masks_for(rng, n, L, 128)
+    oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
+    # hm_encrypt_device_into: values + masks already in HBM, into existing batches
+    ca = ctx.encrypt(np.zeros(n, dtype=np.uint32), np.zeros(n * L * 16, dtype=np.uint8))
+    cb = ca.clone()
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x).view(np.uint8).copy()).cuda()
+    for batch, v, m in ((ca, a, ma), (cb, b, mb)):
+        dv, dm = dev(v), dev(m)
+        torch.cuda.synchronize()
+        assert lib.hm_encrypt_device_into(ctx._h, dv.data_ptr(), n, L, dm.data_ptr(), batch._h) == 0
+        ctx.synchronize()
+    fresh_w = [5] * L
+    np.testing.assert_array_equal(ca.to_host(), expected_padded(oa, n, fresh_w))
+    np.testing.assert_array_equal(cb.to_host(), expected_padded(ob, n, fresh_w))
+    assert lib.hm_encrypt_device_into(ctx._h, dv.data_ptr(), n + 1, L, dm.data_ptr(), cb._h) == N.HM_ERR_INVALID_ARGUMENT
+    # hm_apply2_into for ADD (dispatches to the warp kernel at this size), AND, XOR
+    for op, oop in ((hm.HomomorphicAddition, oracle.OP_ADD), (hm.HomomorphicAndGate, oracle.OP_AND), (hm.HomomorphicXorGate, oracle.OP_XOR)):
+        out = ctx.apply2(op, ca, cb)
+        want, _ = oracle.apply(oop, oa, ob, L, threads=oracle.max_threads())
+        exp = expected_padded(want, n, out.slot_words())
+        # overwrite the result with garbage, then recompute in place
+        junk = ctx.upload(np.full_like(exp, 0xDEADBEEFCAFEF00D), [int(w) for w in out.slot_words()], [int(x) for x in out.slot_degree_bounds()])
+        assert lib.hm_apply2_into(ctx._h, op.code, ca._h, cb._h, junk._h) == 0
+        np.testing.assert_array_equal(junk.to_host(), exp)
+        # a result batch of the wrong shape is refused
+        if op is not hm.HomomorphicXorGate:
+            assert lib.hm_apply2_into(ctx._h, op.code, ca._h, cb._h, ca._h) == N.HM_ERR_INVALID_ARGUMENT
+        if op is hm.HomomorphicAddition:
+            # hm_decrypt_device on the ragged result and on a fresh batch
+            dout = torch.zeros(n * 4, dtype=torch.uint8, device="cuda")
+            assert lib.hm_decrypt_device(ctx._h, junk._h, dout.data_ptr()) == 0
+            ctx.synchronize()
+            od, _ = oracle.decrypt(sk, want, L)
+            np.testing.assert_array_equal(dout.cpu().numpy(), od)
+            np.testing.assert_array_equal(dout.cpu().numpy().view(np.uint32), a + b)
+        junk.free()
+        out.free()
+    ca2, cb2 = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    dout = torch.zeros(n * 4, dtype=torch.uint8, device="cuda")
+    assert lib.hm_decrypt_device(ctx._h, ca2._h, dout.data_ptr()) == 0
+    ctx.synchronize()
+    np.testing.assert_array_equal(dout.cpu().numpy().view(np.uint32), a)
+    # hm_poly_mulrem_into: n * L fresh pairs -> d-bit remainders
+    mr = ctx.poly_mulrem(ca2, cb2)
+    want, _ = oracle.poly_mulrem(oa, ob, sk, threads=oracle.max_threads())
+    exp = expected_padded(want, n, mr.slot_words())
+    junk = ctx.upload(np.full_like(exp, 0x5555AAAA5555AAAA), [int(w) for w in mr.slot_words()], [int(x) for x in mr.slot_degree_bounds()])
+    assert lib.hm_poly_mulrem_into(ctx._h, ca2._h, cb2._h, junk._h) == 0
+    np.testing.assert_array_equal(junk.to_host(), exp)
+    np.testing.assert_array_equal(mr.to_host(), exp)
+    assert lib.hm_poly_mulrem_into(ctx._h, ca2._h, cb2._h, ca2._h) == N.HM_ERR_INVALID_ARGUMENT
+
+
+def test_upload_canonical_round_trip_and_orphans(oracle, hm):
+    """hm_batch_upload_canonical is the inverse of hm_batch_download_canonical (ragged degrees, null polynomials), rejects
+    inconsistent input, and batches outliving their context can still be freed (they are orphans)."""
+    import ctypes as C
+
+    from homomorph_rust_b200 import _native as N
+
+    rng = np.random.default_rng(5)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 43)
+    lib = hm.lib()
+    n, L = 9, 8
+    a = rng.integers(0, 256, size=n, dtype=np.uint8)
+    b = rng.integers(0, 256, size=n, dtype=np.uint8)
+    ca, cb = ctx.encrypt(a, masks_for(rng, n, L, 128)), ctx.encrypt(b, masks_for(rng, n, L, 128))
+    s = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+    can = s.canonical()
+    back = ctx.upload_canonical(can, n, L, degree_bounds=[int(x) for x in s.slot_degree_bounds()])
+    np.testing.assert_array_equal(back.to_host(), s.to_host())
+    np.testing.assert_array_equal(ctx.decrypt(back, np.uint8), a + b)
+    # without bounds the slots are as wide as the largest degree seen; the polynomials are the same
+    tight = ctx.upload_canonical(can, n, L)
+    assert all(int(w) <= int(w0) for w, w0 in zip(tight.slot_words(), s.slot_words()))
+    assert [(d, list(w)) for d, w in tight.canonical()] == [(d, list(w)) for d, w in can]
+    # a null polynomial is (degree 0, [0]) — src/polynomial.rs:132-137
+    z = ctx.upload_canonical([(0, [0])] * 8, 1, 8)
+    assert not z.to_host().any() and list(z.slot_words()) == [1] * 8
+    # stated degree must be the highest set bit; buffer must be exactly consumed; bounds must cover
+    u64p = C.POINTER(C.c_uint64)
+    out = C.c_void_p()
+    bad = np.array([5, 0b1000], dtype=np.uint64)  # degree 5 stated, true degree 3
+    assert lib.hm_batch_upload_canonical(ctx._h, 1, 1, bad.ctypes.data, 2, None, C.byref(out)) == N.HM_ERR_INVALID_ARGUMENT
+    good = np.array([3, 0b1000], dtype=np.uint64)
+    assert lib.hm_batch_upload_canonical(ctx._h, 1, 1, good.ctypes.data, 1, None, C.byref(out)) == N.HM_ERR_INVALID_LENGTH
+    long = np.array([3, 0b1000, 0], dtype=np.uint64)
+    assert lib.hm_batch_upload_canonical(ctx._h, 1, 1, long.ctypes.data, 3, None, C.byref(out)) == N.HM_ERR_INVALID_LENGTH
+    small = np.array([2], dtype=np.uint64)
+    assert lib.hm_batch_upload_canonical(ctx._h, 1, 1, good.ctypes.data, 2, small.ctypes.data_as(u64p), C.byref(out)) == N.HM_ERR_INVALID_ARGUMENT
+    assert lib.hm_batch_upload_canonical(ctx._h, 1, 1, good.ctypes.data, 2, None, C.byref(out)) == 0
+    lib.hm_batch_free(None, out)  # NULL context: the batch knows its owner
+    # orphans: destroy the context first, free the batches afterwards
+    ctx.close()
+    for batch in (ca, cb, s, back, tight, z):
+        batch.free()
