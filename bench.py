@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — BASELINE.json's headline metric on B200: u32 homomorphic adds/s (config 3: ripple-carry
-XOR/AND circuit on 2^18 encrypted pairs per GPU, d=d'=128, delta=1, tau=128), plus the secondary lines
-(GF(2)[X] mul+rem/s, batched encrypt / decrypt) in `extra`.
+XOR/AND circuit on 2^18 encrypted pairs per GPU, d=d'=128, delta=1, tau=128), plus the second half of the metric
+(GF(2)[X] mul+rem/s at d=d'=128, and the d=d'=512 sweep of config 5) and the secondary lines in `extra`.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
@@ -10,10 +10,12 @@ XOR/AND circuit on 2^18 encrypted pairs per GPU, d=d'=128, delta=1, tau=128), pl
 One JSON line on stdout (rank 0).  A "step" is one pass of the fused adder over one batch of 2^18 synthetic
 encrypted pairs per GPU (inputs 2 x 320 MiB, result 11.45 GiB: far larger than the 126 MB L2, so no L2 flush
 is needed between iterations).  `value` is timed with CUDA events on the engine's stream with inputs resident in
-HBM; `e2e` goes through the host-buffer C-ABI call hm_apply2_host (pinned host ciphertexts in, pinned host
-result out, copies inside the timed region).  `--impl reference` times the CPU restatement of the reference
-(oracle/, all host threads) on a bounded sample of the same workload — the reference itself is Rust and cannot
-be built in this image (DESIGN.md "Oracle").
+HBM.  `e2e` goes through the host-buffer C-ABI call hm_apply2_host_bounded (pinned host CIPHERTEXTS in, pinned host
+result out, copies inside the timed region — the drop-in for Context::apply2 on host-resident Ciphered<T>);
+`e2e_circuit` is the flow of the reference's own bench (benches/u32.rs:8-50) with the ciphertexts staying in HBM:
+host plaintexts -> encrypt -> add -> decrypt -> host plaintexts.  `--impl reference` times the CPU restatement of the
+reference (oracle/, all host threads) on a bounded sample of the same workload — the reference itself is Rust and
+cannot be built in this image (DESIGN.md "Oracle").
 """
 from __future__ import annotations
 
@@ -37,14 +39,27 @@ D, DP, DELTA, TAU = 128, 128, 1, 128
 L = 32
 METRIC = "u32 hom. adds/s"
 UNIT = "adds/s"
+WORKLOAD = ("configs[2]: u32 homomorphic add (ripple-carry XOR/AND circuit) on 2^18 encrypted pairs per GPU, "
+            "d=dp=128, delta=1, tau=128")
 # SURVEY.md §8(d) / §A.2 — algorithmic work of one u32 homomorphic add at D = d+d' = 256
 BITMACS_PER_ADD = 2.751e8        # schoolbook AND-XOR pairs over the 93 reference multiplications
 BYTES_PER_ADD = 2560 + 46912     # 2 x 32 x 5 words in, 5 864 words out
 BITMACS_PER_MULREM = 66049 + 49665
 BYTES_PER_MULREM = 96
-# dram__bytes_read.sum + dram__bytes_write.sum of adder_fused_kernel from the ncu --set full capture in profiles/
-# (r01_adder_ncu_details.txt: 42.3 MB + 711.4 MB for 16 384 adds), per add
-NCU_DRAM_BYTES_PER_ADD = (4.277474e9 + 4.852116e9) / 75776  # ncu capture of adder_thread_smem_kernel<4>, profiles/r01_adder_thread_smem_ncu_details.txt
+# Executed instructions of the dominant kernel, from the ncu capture of the shipped adder_chain_kernel<8,0,4>
+# (profiles/r02_adder_chain_ncu.txt: smsp__inst_executed_pipe_{fmaheavy,alu}.sum and dram__bytes_{read,write}.sum of a
+# 75 776-pair launch, divided by 75 776).  Warp-level instructions per add (one thread = one add, so / 32 of the thread count).
+NCU = {
+    "source": "profiles/r02_adder_chain_ncu.txt (ncu --set full + pipe instruction counts, adder_chain_kernel<8,0,4>, 75 776 pairs)",
+    "fmaheavy_warp_instr_per_add": 3076519808 / 75776,   # smsp__inst_executed_pipe_fmaheavy.sum: 40 600 (2 881 products x 432 IMAD.WIDE / 32 = 38 894, + moves)
+    "alu_warp_instr_per_add": 5996560128 / 75776,        # smsp__inst_executed_pipe_alu.sum: 79 135 (LOP3 & co)
+    "all_warp_instr_per_add": 9405915411 / 75776,        # smsp__inst_executed.sum: 124 128
+    "dram_bytes_per_add": (4.104197e9 + 4.721930e9) / 75776,  # dram__bytes_read.sum + dram__bytes_write.sum: 116.5 KB
+    "pipe_pct_at_capture": {"alu": 47.27, "fmaheavy": 47.50, "adds_per_s_at_capture": 75776 / 21.408736e-3,
+                            "note": "sm__pipe_{alu,fmaheavy}_cycles_active.avg.pct_of_peak_sustained_elapsed of the single-wave capture (3.54 M adds/s): "
+                                    "ncu's 100 % is 2.0 (ALU) / 1.02 (IMAD.WIDE) warp-instructions per clock per SM; scale by adds/s for other rates"},
+}
+KARA8_PER_ADD = 1 + 30 * 3 + 6 * 465  # per bit: g (k=0), g, g_lo*p, g_hi*p (k=1..30); chain: sum_k k = 465 chunks x 6
 
 
 def measured_peaks():
@@ -125,17 +140,20 @@ def run_reference(args, rank, world):
     rng = np.random.default_rng(7)
     sk, pk = orc.keygen(D, DP, DELTA, TAU, rng)
 
+    def raw(v):
+        return np.frombuffer(v.astype("<u4").tobytes(), dtype=np.uint8)
+
     def enc(n):
         v = rng.integers(0, 2**32, size=n, dtype=np.uint32)
         m = rng.integers(0, 256, size=n * L * 16, dtype=np.uint8)
-        return orc.encrypt(pk, np.frombuffer(v.astype("<u4").tobytes(), dtype=np.uint8), 4, m, threads=threads)[0]
+        return orc.encrypt(pk, raw(v), 4, m, threads=threads)[0]
 
     # calibrate: one add per thread
     a, b = enc(threads), enc(threads)
     _, sec = orc.apply(orc.OP_ADD, a, b, L, threads=threads)
     rate = threads / max(sec, 1e-9)
     total_steps = args.steps + args.warmup
-    per_step_s = min(8.0, max(1.0, 150.0 / max(total_steps, 1)))
+    per_step_s = min(8.0, max(1.0, 120.0 / max(total_steps, 1)))
     n = max(threads, int(rate * per_step_s) // threads * threads)
     a, b = enc(n), enc(n)
     for _ in range(args.warmup):
@@ -145,17 +163,31 @@ def run_reference(args, rank, world):
         _, sec = orc.apply(orc.OP_ADD, a, b, L, threads=threads)
         t += sec
     value = n * args.steps / t
+    # the whole circuit of benches/u32.rs on the same cores: plaintexts -> encrypt x2 -> add -> decrypt -> plaintexts
+    nc = max(threads, n // 2 // threads * threads)
+    va = rng.integers(0, 2**32, size=nc, dtype=np.uint32)
+    vb = rng.integers(0, 2**32, size=nc, dtype=np.uint32)
+    ma = rng.integers(0, 256, size=nc * L * 16, dtype=np.uint8)
+    mb = rng.integers(0, 256, size=nc * L * 16, dtype=np.uint8)
+    t0 = time.perf_counter()
+    ca, _ = orc.encrypt(pk, raw(va), 4, ma, threads=threads)
+    cb, _ = orc.encrypt(pk, raw(vb), 4, mb, threads=threads)
+    cs, _ = orc.apply(orc.OP_ADD, ca, cb, L, threads=threads)
+    dec, _ = orc.decrypt(sk, cs, L, threads=threads)
+    circuit_s = time.perf_counter() - t0
+    circuit_ok = float(np.mean(dec.view("<u4") == (va + vb)))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64 GF(2) words", "data": "synthetic (seeded keys, plaintexts and subset masks)",
-        "config": {"workload": "configs[2]: u32 homomorphic add (ripple-carry XOR/AND circuit) on 2^18 encrypted pairs per GPU, "
-                               "d=dp=128, delta=1, tau=128", "pairs_per_gpu": 1 << 18, "bits": L,
-                   "pairs_per_step": n, "note": "each step is a bounded sample of the 2^18-pair workload on the host cores; CPU port "
-                                                "of the reference's algorithms (the Rust reference cannot be built in this image)"},
+        "vs_baseline": None, "dtype": "u64 words of GF(2)[X]", "data": "synthetic (seeded keys, plaintexts and subset masks)",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": 1 << 18, "bits": L, "pairs_per_step": n,
+                   "note": "each step is a bounded sample of the 2^18-pair workload on the host cores; CPU port of the reference's "
+                           "algorithms (the Rust reference cannot be built in this image)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n} pairs per step x {args.steps} steps, {threads} threads over independent values"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e_circuit": {"value": nc / circuit_s, "unit": UNIT, "pairs": nc, "seconds": circuit_s, "correct_frac": circuit_ok,
+                        "flow": "plaintexts -> encrypt x2 -> add -> decrypt -> plaintexts, all host threads (benches/u32.rs:8-50)"},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -172,17 +204,25 @@ def run_ours(args, rank, local_rank, world):
     if lib.hm_device_count() <= local_rank:
         raise SystemExit("bench.py: no CUDA device for this rank — the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # pin this rank to the CPUs of its GPU's NUMA node so that pinned host buffers are local to the PCIe root
     # (matters at N > 1 on a two-socket box); restored before the CPU baseline runs
@@ -205,7 +245,7 @@ def run_ours(args, rank, local_rank, world):
     sk, pk = make_keys(hm)  # the public key is replicated on every GPU; no collective on the hot path
     ctx.set_secret_key(sk)
     ctx.set_public_key(pk)
-    stream = torch.cuda.ExternalStream(lib.hm_context_stream(ctx._h), device=torch.device("cuda", local_rank))
+    stream = torch.cuda.ExternalStream(lib.hm_context_stream(ctx._h), device=dev)
 
     n = args.pairs
     rng = np.random.default_rng(1000 + rank)
@@ -214,14 +254,11 @@ def run_ours(args, rank, local_rank, world):
 
     def enc(v, seed):
         g = np.random.default_rng(seed)
-        out = None
-        # masks are host generated (reproducible): 16 B per bit-ciphertext, uploaded in slices
+        # masks are host generated (reproducible): 16 B per bit-ciphertext
         m = np.frombuffer(g.bytes(v.size * L * 16), dtype=np.uint8)
-        out = ctx.encrypt(v, m)
-        return out
+        return ctx.encrypt(v, m)
 
     ca, cb = enc(a, 5000 + rank), enc(b, 6000 + rank)
-    launches0 = ctx.kernel_launches()
     out = ctx.apply2(hm.HomomorphicAddition, ca, cb)  # allocates the 11.45 GiB result once; also a warm-up
 
     def step():
@@ -249,19 +286,16 @@ def run_ours(args, rank, local_rank, world):
     l_after = ctx.kernel_launches()
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = max_over_ranks(total_ms)
     value = world * n * args.steps / (total_ms_max * 1e-3)
 
     # sanity outside the timed region: the decrypted sums (probabilistically exact at delta=1)
     dec = ctx.decrypt(out)
     frac_ok = float(np.mean(dec == (a + b)))
 
-    # ---- end to end through the host-buffer C-ABI call -------------------------------------------------
+    # ---- end to end through the host-buffer C-ABI call (ciphertexts in host memory) ------------------------------
     ne = min(args.e2e_pairs, n)
-    wa = np.full(L, 5, dtype=np.uint32)
+    fresh = np.full(L, D + DP, dtype=np.uint64)
     wo = out.slot_words().astype(np.uint32)
     vwo = int(wo.sum())
     h_a = lib.hm_host_alloc(ne * 160 * 8)
@@ -269,17 +303,16 @@ def run_ours(args, rank, local_rank, world):
     h_o = lib.hm_host_alloc(ne * vwo * 8)
     if not (h_a and h_b and h_o):
         raise RuntimeError("pinned host allocation failed")
-    # pinned copies of the first `ne` encrypted pairs
-    for dst, batch in ((h_a, ca), (h_b, cb)):
+    for dst, batch in ((h_a, ca), (h_b, cb)):  # pinned copies of the first `ne` encrypted pairs
         host = batch.to_host()  # keep the array alive while it is copied
         C.memmove(dst, host.ctypes.data, ne * 160 * 8)
         del host
-    u32p = C.POINTER(C.c_uint32)
+    u64p = C.POINTER(C.c_uint64)
 
     def e2e_step():
-        rc = lib.hm_apply2_host(ctx._h, N.HM_OP_ADD, ne, L, wa.ctypes.data_as(u32p), h_a, wa.ctypes.data_as(u32p), h_b, h_o)
+        rc = lib.hm_apply2_host_bounded(ctx._h, N.HM_OP_ADD, ne, L, fresh.ctypes.data_as(u64p), h_a, fresh.ctypes.data_as(u64p), h_b, h_o)
         if rc != 0:
-            raise RuntimeError(f"hm_apply2_host failed: {rc} {lib.hm_last_error(ctx._h).decode()}")
+            raise RuntimeError(f"hm_apply2_host_bounded failed: {rc} {lib.hm_last_error(ctx._h).decode()}")
 
     for _ in range(4):  # first DMAs into freshly pinned pages are slow (seen: 79, 73, then 58 ms per step), more so with 8 ranks at once
         e2e_step()
@@ -292,11 +325,8 @@ def run_ours(args, rank, local_rank, world):
         e2e_step()
         e2e_step_ms.append((time.perf_counter() - ts) * 1e3)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * ne * e2e_steps / float(te.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * ne * e2e_steps / e2e_s
     # the host result of the last e2e step equals the device result of the timed steps (same inputs)
     host_out = np.ctypeslib.as_array(C.cast(h_o, C.POINTER(C.c_uint64)), shape=(ne, vwo))
     probe = ctx.upload(np.ascontiguousarray(host_out[:64]), [int(x) for x in wo], [int(x) for x in out.slot_degree_bounds()])
@@ -304,43 +334,142 @@ def run_ours(args, rank, local_rank, world):
     probe.free()
     lib.hm_host_free(h_a); lib.hm_host_free(h_b); lib.hm_host_free(h_o)
 
-    # ---- secondary lines (same run, short) ----------------------------------------------------------------
-    extra = {}
-    if rank == 0 and not args.no_extra:
-        def timed(fn, reps=5):
-            fn(); ctx.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(reps):
-                fn()
-            e1.record(stream); ctx.synchronize()
-            return e0.elapsed_time(e1) * 1e-3 / reps
+    # ---- end to end, whole circuit: host plaintexts -> encrypt (device-side masks) -> add -> decrypt -> host plaintexts ----
+    nc = min(args.circuit_pairs, n)
+    hva = torch.from_numpy(a[:nc].copy()).pin_memory()
+    hvb = torch.from_numpy(b[:nc].copy()).pin_memory()
+    hres = torch.zeros(nc, dtype=torch.int32).pin_memory()
 
-        hbm_peak, _ = measured_peaks()
-        # mul+rem on fresh pairs: every slot of (ca, cb) is one pair -> n*32 pairs per launch
-        mr = ctx.poly_mulrem(ca, cb)
+    def circuit_step(seed):
+        ea, eb, es = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        rc = lib.hm_encrypt_seeded(ctx._h, hva.data_ptr(), nc, L, seed, C.byref(ea))
+        rc = rc or lib.hm_encrypt_seeded(ctx._h, hvb.data_ptr(), nc, L, seed + 1, C.byref(eb))
+        rc = rc or lib.hm_apply2(ctx._h, N.HM_OP_ADD, ea, eb, C.byref(es))
+        rc = rc or lib.hm_decrypt(ctx._h, es, hres.data_ptr())
+        for h in (ea, eb, es):
+            if h.value:
+                lib.hm_batch_free(ctx._h, h)
+        if rc != 0:
+            raise RuntimeError(f"circuit step failed: {rc} {lib.hm_last_error(ctx._h).decode()}")
+
+    circuit_step(100); circuit_step(200)
+    ctx.synchronize()
+    barrier()
+    c_steps = max(1, min(args.steps, 3))
+    lc0 = ctx.kernel_launches()
+    t0 = time.perf_counter()
+    c_ms = []
+    for i in range(c_steps):
+        ts = time.perf_counter()
+        circuit_step(1000 + 2 * i)
+        c_ms.append((time.perf_counter() - ts) * 1e3)
+    barrier()
+    c_s = max_over_ranks(time.perf_counter() - t0)
+    circuit_value = world * nc * c_steps / c_s
+    circuit_launches = int(ctx.kernel_launches() - lc0)
+    circuit_ok = float(np.mean(hres.numpy().view(np.uint32) == (a[:nc] + b[:nc])))
+    del hva, hvb, hres
+
+    # ---- the box's PCIe ceiling with every rank copying at once (what bounds `e2e` at N > 1) -----------------------------
+    pcie = {}
+    hp = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+    dp_ = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    for name, src, dst in (("h2d", hp, dp_), ("d2h", dp_, hp)):
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        mine = time.perf_counter() - t0
+        pcie[name + "_GBps_this_rank"] = 3 * (1 << 30) / mine / 1e9
+        pcie[name + "_GBps_all_ranks_concurrent"] = world * 3 * (1 << 30) / max_over_ranks(mine) / 1e9
+    del hp, dp_
+    pcie["note"] = ("every rank copies 1 GiB of pinned memory at the same time (barrier before, max over ranks): the measured "
+                    "aggregate host<->device rate of this box, the ceiling of any host-buffer call at this N")
+    e2e_bytes_per_s = e2e_value * (46912 + 2560)
+    pcie["e2e_d2h_frac_of_concurrent_ceiling"] = e2e_value * 46912 / 1e9 / pcie["d2h_GBps_all_ranks_concurrent"]
+
+    # ---- second half of BASELINE's metric on EVERY rank: fused (a*b) mod S on fresh pairs --------------------------------
+    extra = {}
+    hbm_peak, hbm_src = measured_peaks()
+
+    def timed(fn, reps=5, strm=None, sync=None):
+        strm = strm or stream
+        sync = sync or ctx.synchronize
+        fn(); sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(strm)
+        for _ in range(reps):
+            fn()
+        e1.record(strm); sync()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    if not args.no_extra:
+        mr = ctx.poly_mulrem(ca, cb)  # every slot of (ca, cb) is one pair -> n*32 pairs per launch
+
         def mulrem():
             rc = lib.hm_poly_mulrem_into(ctx._h, ca._h, cb._h, mr._h)
             assert rc == 0, rc
-        s = timed(mulrem)
+
+        barrier()
+        s_mr = max_over_ranks(timed(mulrem))
         pairs = n * L
-        lane_ops = C.c_double(0.0)
-        lib.hm_measure_alu_peak(ctx._h, C.byref(lane_ops), None)
-        extra["mulrem"] = {"metric": "GF(2)[X] mul+rem/s (d=d'=128)", "value": pairs / s, "unit": "mul+rem/s",
-                           "kernel": "mulrem_fresh_a_kernel<1024>", "pairs_per_launch": pairs, "ms": s * 1e3,
-                           "hbm_GBps": pairs * BYTES_PER_MULREM / s / 1e9, "hbm_frac": pairs * BYTES_PER_MULREM / s / 1e9 / hbm_peak,
-                           "Tbitmac_per_s": pairs * BITMACS_PER_MULREM / s / 1e12,
-                           "alu_frac": pairs * BITMACS_PER_MULREM / s / (lane_ops.value * 32.0)}
-        k8m = C.c_double(0.0)
-        lib.hm_measure_kara8_peak(ctx._h, C.byref(k8m))
-        # the kernel reduces both operands mod S first, so its product is 4x4 words = 9 leaf products (an 8x8-word Karatsuba is 27):
-        # what is left is mostly the three table folds (14 words x 4 lookups per pair)
-        extra["mulrem"]["product_pipe_frac"] = pairs / 3.0 / s / k8m.value
-        extra["mulrem"]["note"] = ("(a b) mod S computed as ((a mod S)(b mod S)) mod S: same remainder bit for bit, a third of the leaf "
-                                   "products; 10.3 G/s with the full 8x8-word product first")
+        extra["mulrem"] = {"metric": "GF(2)[X] mul+rem/s (d=d'=128)", "value": world * pairs / s_mr, "unit": "mul+rem/s", "n_gpus": world,
+                           "kernel": "mulrem_fresh_a_kernel<1024>", "pairs_per_launch_per_gpu": pairs, "ms": s_mr * 1e3,
+                           "hbm_GBps_per_gpu": pairs * BYTES_PER_MULREM / s_mr / 1e9, "hbm_frac": pairs * BYTES_PER_MULREM / s_mr / 1e9 / hbm_peak,
+                           "Tbitmac_per_s_per_gpu": pairs * BITMACS_PER_MULREM / s_mr / 1e12,
+                           "note": "(a b) mod S computed as ((a mod S)(b mod S)) mod S: same remainder bit for bit, a third of the leaf products; "
+                                   "every rank runs it on its own shard, time = max over ranks, value = aggregate"}
         mr.free()
-        # decrypt after add (HBM bound: 46 912 B per value)
-        dout = torch.empty(n * 4, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        # config 5 (stress): d=d'=512, tau=256, delta=8 fused mul+rem, swept over 2^10 .. 2^22 fresh pairs per GPU
+        rb = np.random.default_rng(55)
+        ctxb = hm.Context(hm.Parameters(512, 512, 8, 256), device=local_rank)
+        skb = hm.SecretKey.random(512, rb)
+        ctxb.set_secret_key(skb)
+        ctxb.set_public_key(hm.PublicKey.random(512, 8, 256, skb, rb))
+        streamb = torch.cuda.ExternalStream(lib.hm_context_stream(ctxb._h), device=dev)
+        sweep = []
+        top = args.sweep_max_log2
+        nb = (1 << top) // 8  # u8 values -> 8 pairs each
+        vb1 = rb.integers(0, 256, size=nb, dtype=np.uint8)
+        vb2 = rb.integers(0, 256, size=nb, dtype=np.uint8)
+        cb1 = ctxb.encrypt(vb1, seed=77 + rank)
+        cb2 = ctxb.encrypt(vb2, seed=99 + rank)
+        for lg in range(10, top + 1, 2):
+            cnt = (1 << lg) // 8
+            if cnt != nb:  # a prefix of the same plaintexts, encrypted again (cheap; batches have no sub-range views)
+                s1 = ctxb.encrypt(vb1[:cnt], seed=77 + rank)
+                s2 = ctxb.encrypt(vb2[:cnt], seed=99 + rank)
+            else:
+                s1, s2 = cb1, cb2
+            mrb = ctxb.poly_mulrem(s1, s2)
+
+            def mulrem_b():
+                assert lib.hm_poly_mulrem_into(ctxb._h, s1._h, s2._h, mrb._h) == 0
+
+            barrier()
+            reps = 20 if lg <= 16 else 5
+            sb = max_over_ranks(timed(mulrem_b, reps=reps, strm=streamb, sync=ctxb.synchronize))
+            sweep.append({"log2_pairs_per_gpu": lg, "value": world * (cnt * 8) / sb, "unit": "mul+rem/s", "ms": sb * 1e3})
+            mrb.free()
+            if cnt != nb:
+                s1.free(); s2.free()
+        big = sweep[-1]
+        extra["mulrem_config_b"] = {"metric": "GF(2)[X] mul+rem/s (d=d'=512, tau=256, delta=8)", "value": big["value"], "unit": "mul+rem/s", "n_gpus": world,
+                                    "kernel": "mulrem_fresh32q_kernel", "pairs_per_launch_per_gpu": 1 << top, "ms": big["ms"],
+                                    "Tbitmac_per_s_per_gpu": (1 << top) * (1050625 + 788481) / (big["ms"] * 1e-3) / 1e12,
+                                    "sweep": sweep,
+                                    "note": "configs[4]: carry-less mul + rem sweep; operands reduced mod S first (sliding-window table folds from shared "
+                                            "memory), then a 16-word product (three 8x8-word Karatsubas) and one more fold; aggregate over ranks, "
+                                            "small batches are launch-latency bound"}
+        for ob in (cb1, cb2):
+            ob.free()
+        ctxb.close()
+
+    # ---- secondary lines (rank 0 only, short) ------------------------------------------------------------------------------
+    if rank == 0 and not args.no_extra:
+        dout = torch.empty(n * 4, dtype=torch.uint8, device=dev)
         s = timed(lambda: lib.hm_decrypt_device(ctx._h, out._h, dout.data_ptr()))
         extra["decrypt_after_add"] = {"value": n / s, "unit": "u32/s", "kernel": "decrypt_value_tma_kernel<2,256> x 2 CTAs/SM", "ms": s * 1e3,
                                       "hbm_GBps": n * 46912 / s / 1e9, "hbm_frac": n * 46912 / s / 1e9 / hbm_peak}
@@ -350,35 +479,39 @@ def run_ours(args, rank, local_rank, world):
                                   "note": "320 MiB of ciphertext per launch (> 126 MB L2)"}
         # encrypt with values + masks already in HBM, into an existing batch
         g = np.random.default_rng(1)
-        dm = torch.from_numpy(np.frombuffer(g.bytes(n * L * 16), dtype=np.uint8).copy()).to(f"cuda:{local_rank}")
-        dv = torch.from_numpy(a.view(np.uint8).copy()).to(f"cuda:{local_rank}")
+        dm = torch.from_numpy(np.frombuffer(g.bytes(n * L * 16), dtype=np.uint8).copy()).to(dev)
+        dv = torch.from_numpy(a.view(np.uint8).copy()).to(dev)
         ce = ca.clone()
+
         def encd():
             rc = lib.hm_encrypt_device_into(ctx._h, dv.data_ptr(), n, L, dm.data_ptr(), ce._h)
             assert rc == 0, rc
+
         s = timed(encd, reps=20)
-        # shared-memory side of the same kernel: 15 rotated + 1 plain warp-wide LDS.64 per 6 bit-ciphertexts, 2 wavefronts
-        # (128 B each) per LDS.64 -> 32 / 6 shared-memory cycles per bit-ciphertext per SM at best
         props = torch.cuda.get_device_properties(local_rank)
-        sm_count, sm_clk = props.multi_processor_count, getattr(props, "clock_rate", 1965000) * 1e3  # max SM clock; the run's clocks are in "clocks"
+        sm_count, sm_clk = props.multi_processor_count, getattr(props, "clock_rate", 1965000) * 1e3
         extra["encrypt"] = {"value": n / s, "unit": "u32/s", "kernel": "encrypt_tab6b_kernel", "ms": s * 1e3,
                             "hbm_GBps": n * 1792 / s / 1e9, "hbm_frac": n * 1792 / s / 1e9 / hbm_peak,
                             "smem_frac": (n * L / s) * (32.0 / 6.0) / (sm_count * sm_clk),
                             "note": "table lookups: 640 B of shared-memory reads per 56 B of HBM traffic, so the binding roofline is the "
                                     "shared-memory pipe (smem_frac = LDS wavefront cycles needed / available), not HBM"}
         ce.free()
+        del dm, dv
         # end-to-end encryption, host plaintexts in -> ciphertexts resident in HBM: (i) host-generated masks cross PCIe
         # (16 B per bit), (ii) masks generated on the device from a seed (Philox4x32-10), only 4 B per u32 cross
         hv = torch.from_numpy(a.copy()).pin_memory()
         hm_ = torch.from_numpy(np.frombuffer(np.random.default_rng(2).bytes(n * L * 16), dtype=np.uint8).copy()).pin_memory()
+
         def e2e_enc_masks():
             o = C.c_void_p()
             assert lib.hm_encrypt(ctx._h, hv.data_ptr(), n, L, hm_.data_ptr(), C.byref(o)) == 0
             lib.hm_batch_free(ctx._h, o)
+
         def e2e_enc_seed():
             o = C.c_void_p()
             assert lib.hm_encrypt_seeded(ctx._h, hv.data_ptr(), n, L, 12345, C.byref(o)) == 0
             lib.hm_batch_free(ctx._h, o)
+
         for name, fn in (("encrypt_e2e_host_masks", e2e_enc_masks), ("encrypt_e2e_seeded", e2e_enc_seed)):
             fn(); ctx.synchronize()
             times = []
@@ -399,8 +532,7 @@ def run_ours(args, rank, local_rank, world):
         ao = ctx.apply2(hm.HomomorphicAndGate, ca, cb)
         s = timed(lambda: lib.hm_apply2_into(ctx._h, N.HM_OP_AND, ca._h, cb._h, ao._h), reps=5)
         extra["and_gate"] = {"value": n * L / s, "unit": "bit-ciphertext ands/s", "kernel": "mul_small_kernel<8,8>", "ms": s * 1e3,
-                             "hbm_GBps": n * L * 152 / s / 1e9, "Tbitmac_per_s": n * L * 66049 / s / 1e12,
-                             "alu_frac": n * L * 66049 / s / (lane_ops.value * 32.0)}
+                             "hbm_GBps": n * L * 152 / s / 1e9, "Tbitmac_per_s": n * L * 66049 / s / 1e12}
         s = timed(lambda: lib.hm_apply2_into(ctx._h, N.HM_OP_OR, ca._h, cb._h, ao._h), reps=5)
         extra["or_gate"] = {"value": n * L / s, "unit": "bit-ciphertext ors/s", "kernel": "mul_small_kernel<8,8> (a + b + a*b fused)", "ms": s * 1e3,
                             "hbm_GBps": n * L * 152 / s / 1e9}
@@ -433,87 +565,82 @@ def run_ours(args, rank, local_rank, world):
         extra["u8_mul"] = {"value": n8 / (t2 - t1), "unit": "u8 muls/s", "pairs": n8, "ms": (t2 - t1) * 1e3, "first_call_ms": (t1 - t0) * 1e3,
                            "ms_each": [round(x * 1e3, 3) for x in t8],
                            "kernel_launches": int(l1 - l0), "correct_frac": float(np.mean(d8 == a8 * b8)),
-                           "note": "column-batched circuit: per column one prefix-XOR launch + one batch of independent carry products (mul_small on a side stream, mul_thread32 for the big ones) over a per-value arena in HBM; wall clock incl. launches, median of 5 after 3 warm-up calls"}
+                           "note": "configs[3] at L = 8 (u32 multiplication is infeasible by construction, SURVEY.md A.3): column-batched circuit over a "
+                                   "per-value arena in HBM; wall clock incl. launches, median of 5 after 3 warm-up calls"}
         for o8 in (p8, p8b, c8a, c8b):
             o8.free()
-        # config 5 (stress): d=d'=512, tau=256, delta=8 fused mul+rem on 2^20 fresh pairs
-        rb = np.random.default_rng(55)
-        ctxb = hm.Context(hm.Parameters(512, 512, 8, 256), device=local_rank)
-        skb = hm.SecretKey.random(512, rb)
-        ctxb.set_secret_key(skb)
-        ctxb.set_public_key(hm.PublicKey.random(512, 8, 256, skb, rb))
-        nb = 1 << 17  # u8 values -> 2^20 pairs
-        vb1 = rb.integers(0, 256, size=nb, dtype=np.uint8)
-        vb2 = rb.integers(0, 256, size=nb, dtype=np.uint8)
-        cb1 = ctxb.encrypt(vb1, np.frombuffer(rb.bytes(nb * 8 * 32), dtype=np.uint8))
-        cb2 = ctxb.encrypt(vb2, np.frombuffer(rb.bytes(nb * 8 * 32), dtype=np.uint8))
-        mrb = ctxb.poly_mulrem(cb1, cb2)
-        streamb = torch.cuda.ExternalStream(lib.hm_context_stream(ctxb._h), device=torch.device("cuda", local_rank))
-        ctxb.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(streamb)
-        for _ in range(5):
-            assert lib.hm_poly_mulrem_into(ctxb._h, cb1._h, cb2._h, mrb._h) == 0
-        e1.record(streamb)
-        ctxb.synchronize()
-        sb = e0.elapsed_time(e1) * 1e-3 / 5
-        extra["mulrem_config_b"] = {"metric": "GF(2)[X] mul+rem/s (d=d'=512, tau=256, delta=8)", "value": nb * 8 / sb, "unit": "mul+rem/s",
-                                    "kernel": "mulrem_fresh32q_kernel", "pairs_per_launch": nb * 8, "ms": sb * 1e3,
-                                    "Tbitmac_per_s": nb * 8 * (1050625 + 788481) / sb / 1e12,
-                                    "alu_frac": nb * 8 * (1050625 + 788481) / sb / (lane_ops.value * 32.0),
-                                    "product_pipe_frac": 3 * nb * 8 / sb / k8m.value,  # three 8x8-word products per pair (+ the table folds)
-                                    "note": "operands reduced mod S first (sliding-window table folds from shared memory), then a 16-word product "
-                                            "(three 8x8-word Karatsubas) and one more fold; the fully unrolled first kernel did 275 M/s, the rolled "
-                                            "32-word product followed by one fold 720 M/s, reduce-first with conflicting table lookups 1.2-1.35 G/s"}
-        for ob in (cb1, cb2, mrb):
-            ob.free()
-        ctxb.close()
-        # PCIe copy rates of this box (the ceiling of every host-buffer call)
-        hp = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
-        dp_ = torch.empty(1 << 30, dtype=torch.uint8, device=f"cuda:{local_rank}")
-        for name, src, dst in (("h2d_GBps", hp, dp_), ("d2h_GBps", dp_, hp)):
-            dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                dst.copy_(src, non_blocking=True)
-            torch.cuda.synchronize()
-            extra[name] = 3 * (1 << 30) / (time.perf_counter() - t0) / 1e9
-        del hp, dp_
-        extra["e2e_pcie_frac"] = (e2e_value / world) * 46912 / 1e9 / extra["d2h_GBps"]
 
-    # ---- roofline of the dominant kernel (adder_fused_kernel: one launch per step) ---------------------------
+    # ---- roofline of the dominant kernel (one adder_chain_kernel launch per step) --------------------------------------------
     roofline = roofline_hbm = None
     if rank == 0:
-        lane_ops = C.c_double(0.0); mhz = C.c_double(0.0)
-        lib.hm_measure_alu_peak(ctx._h, C.byref(lane_ops), C.byref(mhz))
+        props = torch.cuda.get_device_properties(local_rank)
+        sm_count = props.multi_processor_count
         launch_s = float(np.mean(step_ms)) * 1e-3
-        peak_bitmac = lane_ops.value * 32.0
-        ach = n * BITMACS_PER_ADD / launch_s
+        adds_per_s = n / launch_s
+        sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+        pp = (C.c_double * 12)()
+        probes = None
+        probe_clocks = None
+        for attempt in range(2):  # probes whose nvidia-smi clock was below 95 % of the maximum SM clock are taken again once
+            ps = ClockSampler(local_rank)
+            ps.start()
+            time.sleep(0.3)
+            tp0 = time.time()
+            rcp = lib.hm_measure_pipe_peaks(ctx._h, 150.0, pp)
+            probe_clocks = ps.stop(tp0, time.time())
+            if rcp != 0:
+                break
+            probes = {name: {"warp_instr_per_s": pp[4 * i], "ms": pp[4 * i + 1], "warps_per_sm": int(pp[4 * i + 2]),
+                             "warp_instr_per_clk_per_sm": pp[4 * i] / sm_count / ((probe_clocks.get("sm_mhz") or sm_max) * 1e6),
+                             "cycle_counter_mhz_not_the_sm_clock": pp[4 * i + 3]}
+                      for i, name in enumerate(("imad_wide_rr", "lop3_rrr", "mix_1w_2l"))}
+            if (probe_clocks.get("sm_mhz") or 0) >= 0.95 * sm_max:
+                break
         k8 = C.c_double(0.0)
         lib.hm_measure_kara8_peak(ctx._h, C.byref(k8))
-        KARA8_PER_ADD = 1 + 30 * 3 + 6 * 465  # per bit: g (k=0), g, g_lo*p, g_hi*p (k=1..30); chain: sum_k ceil((24k-7)/24) = 465 chunks x 6
-        k8_ach = n * KARA8_PER_ADD / launch_s
-        # The binding unit of this kernel is the integer multiplier (FMA-heavy pipe): the adder is a chain of 8x8-word
-        # Karatsuba products, 432 IMAD.WIDE each.  frac = products/s achieved / the same product timed in isolation.
-        roofline = {"kernel": "adder_thread_smem_kernel<4> (thread-per-value Karatsuba on IMAD.WIDE + LOP3, operands staged in shared memory by cp.async)", "bound": "alu",
-                    "bound_detail": "fma-heavy pipe (integer multiplier): 432 IMAD.WIDE per 8x8-word Karatsuba product, 2 881 products per add",
-                    "achieved": k8_ach / 1e9, "peak": k8.value / 1e9, "unit": "G 8x8-word products/s", "frac": k8_ach / k8.value, "traffic": None,
-                    "peak_source": "measured in this run: hm_measure_kara8_peak (the product in isolation, 16 warps/SM)",
-                    "pipes_busy_ncu": {"alu": 0.58, "fmaheavy": 0.58, "issue_slots": 0.46,
-                                       "source": "profiles/r01_adder_thread_smem_ncu_details.txt (75 776 adds)"},
-                    "lop3_equivalent": {"achieved": ach / 1e12, "peak": peak_bitmac / 1e12, "unit": "Tbit-MAC/s", "frac": ach / peak_bitmac,
-                                        "peak_source": f"measured in this run: LOP3 issue-rate probe, {lane_ops.value / 1e12:.2f} T lane-ops/s at ~{mhz.value:.0f} MHz (x32 bits)",
-                                        "note": "the reference's schoolbook AND-XOR pairs (SURVEY.md A.2) against the LOP3-only issue rate, the "
-                                                "roofline of the first (comb) kernel; Karatsuba on the multiplier does fewer bit operations, "
-                                                "so this ratio exceeds 1"}}
-        roofline["product_pipe"] = {k: roofline[k] for k in ("achieved", "peak", "unit", "frac", "peak_source")}  # earlier name of the same figures
-        hbm_peak, src = measured_peaks()
+        if probes:
+            fma_ach = adds_per_s * NCU["fmaheavy_warp_instr_per_add"]
+            alu_ach = adds_per_s * NCU["alu_warp_instr_per_add"]
+            fma_frac = fma_ach / probes["imad_wide_rr"]["warp_instr_per_s"]
+            alu_frac = alu_ach / probes["lop3_rrr"]["warp_instr_per_s"]
+            busier = "fmaheavy" if fma_frac >= alu_frac else "alu"
+            mix = probes["mix_1w_2l"]
+            roofline = {
+                "kernel": "adder_chain_kernel<8,0,4> (thread-per-value Karatsuba chain on IMAD.WIDE + LOP3, dynamically scheduled work units)",
+                "bound": "alu", "bound_detail": "integer pipes of the SM: FMA-heavy (IMAD.WIDE, the 32x32->64 products) and ALU (LOP3); neither HBM nor tensor",
+                "busier_pipe": busier,
+                "achieved": (fma_ach if busier == "fmaheavy" else alu_ach) / 1e9,
+                "peak": (probes["imad_wide_rr"] if busier == "fmaheavy" else probes["lop3_rrr"])["warp_instr_per_s"] / 1e9,
+                "unit": "G warp-instructions/s on the busier pipe", "frac": max(fma_frac, alu_frac),
+                "pipes": {"fmaheavy": {"achieved_G_warp_instr_per_s": fma_ach / 1e9, "peak": probes["imad_wide_rr"]["warp_instr_per_s"] / 1e9, "frac": fma_frac,
+                                       "warp_instr_per_add": NCU["fmaheavy_warp_instr_per_add"]},
+                          "alu": {"achieved_G_warp_instr_per_s": alu_ach / 1e9, "peak": probes["lop3_rrr"]["warp_instr_per_s"] / 1e9, "frac": alu_frac,
+                                  "warp_instr_per_add": NCU["alu_warp_instr_per_add"]}},
+                "peak_source": "measured in this run by hm_measure_pipe_peaks: IMAD.WIDE (both operands in registers) and LOP3 issue probes, >= 150 ms each "
+                               "(fastest of three), every CTA resident; SM clock during the probes sampled with nvidia-smi (`probe_clocks`)",
+                "probe_clocks": probe_clocks,
+                "instruction_counts_source": NCU["source"],
+                "ncu_pipe_pct_scaled_to_this_rate": {k: NCU["pipe_pct_at_capture"][k] * adds_per_s / NCU["pipe_pct_at_capture"]["adds_per_s_at_capture"] / 100.0
+                                                     for k in ("alu", "fmaheavy")},
+                "probes": probes,
+                "joint_issue_ceiling": {
+                    "what": "the two pipes do not issue independently: the probe with the kernel's own mix (1 IMAD.WIDE : 2 LOP3, 8 chains/thread) sustains "
+                            "less than the sum of the single-pipe peaks; this is the ceiling for THIS instruction mix",
+                    "mix_probe_G_warp_instr_per_s": mix["warp_instr_per_s"] / 1e9, "kernel_G_warp_instr_per_s": (fma_ach + alu_ach) / 1e9,
+                    "mix_probe_warp_instr_per_clk_per_sm": mix["warp_instr_per_clk_per_sm"],
+                    "kernel_warp_instr_per_clk_per_sm": (fma_ach + alu_ach) / sm_count / ((clocks or {}).get("sm_mhz") or sm_max) / 1e6,
+                    "frac_of_mix_ceiling": (fma_ach + alu_ach) / mix["warp_instr_per_s"]},
+                "kara8": {"achieved": adds_per_s * KARA8_PER_ADD / 1e9, "peak": k8.value / 1e9, "unit": "G 8x8-word products/s",
+                          "frac": adds_per_s * KARA8_PER_ADD / k8.value if k8.value else None,
+                          "note": "round-1 figure, kept as a sub-object: the 8x8-word Karatsuba product (432 IMAD.WIDE + 854 LOP3) timed in isolation; "
+                                  "2 881 such products per add"},
+                "traffic": n * NCU["dram_bytes_per_add"],
+                "traffic_source": NCU["source"] + "; algorithmic bytes per launch = %d" % (n * BYTES_PER_ADD),
+            }
         gbs = n * BYTES_PER_ADD / launch_s / 1e9
-        roofline_hbm = {"kernel": "adder_thread_smem_kernel<4>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": gbs / hbm_peak, "traffic": (n * NCU_DRAM_BYTES_PER_ADD) if NCU_DRAM_BYTES_PER_ADD else None,
-                        "traffic_source": "ncu --set full capture (profiles/r01_adder_thread_smem_ncu_details.txt), scaled per add; "
-                                          "algorithmic bytes per launch = %d" % (n * BYTES_PER_ADD),
-                        "peak_source": src}
+        roofline_hbm = {"kernel": "adder_chain_kernel<8,0,4>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": gbs / hbm_peak, "traffic": n * NCU["dram_bytes_per_add"], "peak_source": hbm_src,
+                        "note": "the same kernel against the HBM roofline: far from it, the kernel is integer-pipe bound"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the box's host cores ------------------
     cpu = None
@@ -578,15 +705,23 @@ def run_ours(args, rank, local_rank, world):
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 words of GF(2)[X] (bit-packed; carry-less products on IMAD.WIDE + LOP3)",
             "data": "synthetic (seeded keys, uniform u32 plaintexts, host-generated subset masks)",
-            "config": {"workload": "configs[2]: u32 homomorphic add (ripple-carry XOR/AND circuit) on 2^18 encrypted pairs per GPU, "
-                                   "d=dp=128, delta=1, tau=128", "pairs_per_gpu": n, "bits": L,
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": n, "bits": L,
                        "l2": "inputs 2 x %.0f MiB + result %.2f GiB per step >> 126 MB L2 (no flush needed)" % (n * 1280 / 2**20, n * 46912 / 2**30),
                        "sharding": "independent values split by index across ranks; no collective on the data path"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ne * 2560, "d2h_bytes_per_step": ne * vwo * 8,
-                    "pairs_per_step": ne, "steps": e2e_steps, "step_ms": e2e_step_ms, "call": "hm_apply2_host (pinned host ciphertexts in/out, 3-stream chunked pipeline)",
-                    "matches_device_result": e2e_matches},
+                    "pairs_per_step": ne, "pairs_per_step_note": "a quarter of the headline batch (2^16 of 2^18 pairs per GPU per call): 3.07 GB of pinned "
+                                                                  "result per call; the rate is D2H-bound and does not depend on the batch size",
+                    "steps": e2e_steps, "step_ms": e2e_step_ms,
+                    "call": "hm_apply2_host_bounded (pinned host ciphertexts in/out, 3-stream chunked pipeline)",
+                    "matches_device_result": e2e_matches, "bytes_per_s": e2e_bytes_per_s},
+            "e2e_circuit": {"value": circuit_value, "unit": UNIT, "pairs_per_step": nc, "steps": c_steps, "step_ms": c_ms,
+                            "h2d_bytes_per_step": nc * 8, "d2h_bytes_per_step": nc * 4, "gpu_launches": circuit_launches,
+                            "correct_frac": circuit_ok,
+                            "flow": "host plaintexts -> hm_encrypt_seeded x2 -> hm_apply2(ADD) -> hm_decrypt -> host plaintexts; ciphertexts stay in HBM "
+                                    "(benches/u32.rs:8-50 as one batch); allocation and release of the 11.45 GiB result inside the timed region"},
+            "pcie": pcie,
             "gpu_launches": int(l_after - l_before),
-            "kernels_in_step": ["adder_thread_smem_kernel<4>"],
+            "kernels_in_step": ["adder_chain_kernel<8,0,4>"],
             "clocks": clocks,
             "roofline": roofline, "roofline_hbm": roofline_hbm,
             "cpu_baseline": cpu,
@@ -606,7 +741,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1 << 18, help="encrypted u32 pairs per GPU per step")
-    ap.add_argument("--e2e-pairs", type=int, default=1 << 16, help="pairs per end-to-end step (pinned host buffers)")
+    ap.add_argument("--e2e-pairs", type=int, default=1 << 16, help="pairs per end-to-end step (pinned host ciphertext buffers)")
+    ap.add_argument("--circuit-pairs", type=int, default=1 << 18, help="pairs per whole-circuit end-to-end step (host plaintexts in/out)")
+    ap.add_argument("--sweep-max-log2", type=int, default=22, help="largest batch of the config-5 mul+rem sweep, log2 of pairs per GPU")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

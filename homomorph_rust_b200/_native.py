@@ -31,7 +31,7 @@ HM_OP_AND, HM_OP_OR, HM_OP_XOR, HM_OP_NOT, HM_OP_ADD, HM_OP_MUL = range(6)
 
 def build(force: bool = False) -> str:
     """Compile csrc/ into libhmgpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("hmgpu.cu", "kernels_b.cu", "kernels_adder.cu", "kernels_adder.h", "kernels.cuh", "gf2_blocks.cuh", "gf2host.hpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("hmgpu.cu", "kernels_b.cu", "kernels_adder.cu", "kernels_adder.h", "probes.cu", "probes.h", "hmgroup.cu", "kernels.cuh", "gf2_blocks.cuh", "gf2host.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "hmgpu.h"))
     stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
     if force or stale:
@@ -102,6 +102,28 @@ def lib() -> C.CDLL:
         "hm_masks_generate_host": (C.c_int, [u16, sz, C.c_uint64, vp]),
         "hm_masks_generate_device": (C.c_int, [vp, sz, C.c_uint64, vp]),
         "hm_encrypt_seeded": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint64, C.POINTER(vp)]),
+        "hm_encrypt_seeded_at": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(vp)]),
+        "hm_encrypt_async": (C.c_int, [vp, vp, sz, C.c_uint32, vp, C.POINTER(vp)]),
+        "hm_decrypt_async": (C.c_int, [vp, vp, vp]),
+        "hm_shard_range": (C.c_int, [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz)]),
+        "hm_group_create": (C.c_int, [u16, u16, u16, u16, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+        "hm_group_destroy": (None, [vp]),
+        "hm_group_size": (C.c_int, [vp]),
+        "hm_group_context": (vp, [vp, C.c_int]),
+        "hm_group_set_secret_key": (C.c_int, [vp, vp, sz]),
+        "hm_group_set_public_key": (C.c_int, [vp, C.POINTER(vp), C.POINTER(sz), sz]),
+        "hm_group_synchronize": (C.c_int, [vp]),
+        "hm_group_encrypt": (C.c_int, [vp, vp, sz, C.c_uint32, vp, C.POINTER(vp)]),
+        "hm_group_encrypt_seeded": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint64, C.POINTER(vp)]),
+        "hm_group_apply2": (C.c_int, [vp, C.c_int, vp, vp, C.POINTER(vp)]),
+        "hm_group_apply2_into": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "hm_group_apply1": (C.c_int, [vp, C.c_int, vp]),
+        "hm_group_decrypt": (C.c_int, [vp, vp, vp]),
+        "hm_group_batch_download": (C.c_int, [vp, vp, vp]),
+        "hm_group_batch_len": (sz, [vp]),
+        "hm_group_batch_bits": (C.c_uint32, [vp]),
+        "hm_group_batch_part": (vp, [vp, C.c_int]),
+        "hm_group_batch_free": (None, [vp]),
         "hm_decrypt": (C.c_int, [vp, vp, vp]),
         "hm_decrypt_device": (C.c_int, [vp, vp, vp]),
         "hm_apply2": (C.c_int, [vp, C.c_int, vp, vp, C.POINTER(vp)]),
@@ -111,6 +133,7 @@ def lib() -> C.CDLL:
         "hm_apply2_into": (C.c_int, [vp, C.c_int, vp, vp, vp]),
         "hm_measure_alu_peak": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "hm_measure_kara8_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
+        "hm_measure_pipe_peaks": (C.c_int, [vp, C.c_double, C.POINTER(C.c_double)]),
         "hm_op_min_d_over_delta": (C.c_int, [C.c_int]),
         "hm_result_slot_words": (C.c_int, [vp, C.c_int, C.c_uint32, u32p, u32p, u32p]),
         "hm_apply2_host": (C.c_int, [vp, C.c_int, sz, C.c_uint32, u32p, vp, u32p, vp, vp]),

@@ -563,3 +563,138 @@ class Context:
 
     def kernel_launches(self) -> int:
         return N.lib().hm_context_kernel_launches(self._h)
+
+
+class GroupCiphered:
+    """One logical batch whose values are split by index over the devices of a ContextGroup."""
+
+    def __init__(self, group: "ContextGroup", handle: int, dtype=None):
+        self._g = group
+        self._h = C.c_void_p(handle)
+        self.dtype = dtype
+
+    def __len__(self) -> int:
+        return int(N.lib().hm_group_batch_len(self._h))
+
+    @property
+    def bits(self) -> int:
+        return int(N.lib().hm_group_batch_bits(self._h))
+
+    def part_len(self, i: int) -> int:
+        return int(N.lib().hm_batch_len(N.lib().hm_group_batch_part(self._h, i)))
+
+    def slot_words(self) -> np.ndarray:
+        p = N.lib().hm_group_batch_part(self._h, 0)
+        out = np.zeros(self.bits, dtype=np.uint32)
+        _check(None, N.lib().hm_batch_slot_words(p, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def to_host(self) -> np.ndarray:
+        """(n, value_words) u64, index order — the concatenation of the shards."""
+        vw = int(self.slot_words().sum())
+        out = np.zeros((len(self), vw), dtype=np.uint64)
+        _check(None, N.lib().hm_group_batch_download(self._g._h, self._h, out.ctypes.data))
+        return out
+
+    def free(self) -> None:
+        if self._h is not None and self._h.value:
+            N.lib().hm_group_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ContextGroup:
+    """A Context replicated over several GPUs of one box (include/hmgpu.h "Device groups"): keys and tables on every
+    device, batches split by value index into contiguous ranges, no collective — ciphertexts are independent
+    (reference src/cipher.rs:180-185, :227-237)."""
+
+    def __init__(self, parameters: Parameters, devices: Sequence[int]):
+        self._params = parameters
+        ids = (C.c_int * len(devices))(*[int(x) for x in devices])
+        h = C.c_void_p()
+        rc = N.lib().hm_group_create(parameters.d(), parameters.dp(), parameters.delta(), parameters.tau(), ids, len(devices), C.byref(h))
+        self._h = None
+        if rc == N.HM_ERR_CUDA:
+            raise EngineError(rc, f"no usable CUDA device among {list(devices)} (the engine has no CPU fallback)")
+        _check(None, rc)
+        self._h = h
+        self._sk = self._pk = None
+
+    def __len__(self) -> int:
+        return int(N.lib().hm_group_size(self._h))
+
+    def close(self) -> None:
+        if self._h is not None:
+            N.lib().hm_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_secret_key(self, secret_key: SecretKey) -> None:
+        raw = secret_key.to_bytes()
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        _check(None, N.lib().hm_group_set_secret_key(self._h, C.addressof(buf), len(raw)))
+        self._sk, self._pk = secret_key, None
+
+    def set_public_key(self, public_key: PublicKey) -> None:
+        rows = public_key.to_bytes()
+        bufs = [(C.c_uint8 * len(r)).from_buffer_copy(r) for r in rows]
+        ptrs = (C.c_void_p * len(rows))(*[C.addressof(b) for b in bufs])
+        lens = (C.c_size_t * len(rows))(*[len(r) for r in rows])
+        _check(None, N.lib().hm_group_set_public_key(self._h, ptrs, lens, len(rows)))
+        self._pk = public_key
+
+    def synchronize(self) -> None:
+        _check(None, N.lib().hm_group_synchronize(self._h))
+
+    def encrypt(self, values: np.ndarray, masks: Optional[np.ndarray] = None, seed: Optional[int] = None) -> GroupCiphered:
+        if self._pk is None:
+            raise PublicKeyUnset("PublicKeyUnset")
+        values = np.ascontiguousarray(values)
+        if values.dtype.kind not in "ui":
+            raise TypeError("integers only (bincode fixint little-endian, src/cipher.rs:6-13)")
+        n, L = values.size, values.dtype.itemsize * 8
+        raw = np.frombuffer(values.astype(values.dtype.newbyteorder("<"), copy=False).tobytes(), dtype=np.uint8)
+        out = C.c_void_p()
+        if seed is not None:
+            _check(None, N.lib().hm_group_encrypt_seeded(self._h, raw.ctypes.data, n, L, seed, C.byref(out)))
+        else:
+            if masks is None:
+                raise ValueError("masks or seed")
+            masks = np.ascontiguousarray(masks, dtype=np.uint8).reshape(-1)
+            if masks.size != n * L * ((self._params.tau() + 7) // 8):
+                raise ValueError("masks must hold n * L * ceil(tau/8) bytes")
+            _check(None, N.lib().hm_group_encrypt(self._h, raw.ctypes.data, n, L, masks.ctypes.data, C.byref(out)))
+        return GroupCiphered(self, out.value, values.dtype)
+
+    def apply2(self, op, a: GroupCiphered, b: GroupCiphered) -> GroupCiphered:
+        out = C.c_void_p()
+        rc = N.lib().hm_group_apply2(self._h, op.code, a._h, b._h, C.byref(out))
+        if rc == N.HM_ERR_OPERATION_REQUIREMENT:
+            raise OperationError(op.MIN_D_OVER_DELTA, self._params.d(), self._params.delta())
+        _check(None, rc)
+        return GroupCiphered(self, out.value, a.dtype)
+
+    def apply1(self, op, a: GroupCiphered) -> None:
+        _check(None, N.lib().hm_group_apply1(self._h, op.code, a._h))
+
+    def decrypt(self, c: GroupCiphered, dtype=None) -> np.ndarray:
+        if self._sk is None:
+            raise SecretKeyUnset("SecretKeyUnset")
+        L = c.bits
+        out = np.zeros(len(c) * (L // 8), dtype=np.uint8)
+        rc = N.lib().hm_group_decrypt(self._h, c._h, out.ctypes.data)
+        if rc == N.HM_ERR_INVALID_LENGTH:
+            raise InvalidCipheredLength(f"InvalidCipheredLength {{ len: {L} }}")
+        _check(None, rc)
+        dtype = dtype or c.dtype or np.dtype(f"<u{L // 8}")
+        return out.view(np.dtype(dtype).newbyteorder("<")).astype(dtype)

@@ -22,6 +22,7 @@
 #include "gf2host.hpp"
 #include "kernels.cuh"
 #include "kernels_adder.h"
+#include "probes.h"
 
 namespace hmk {
 cudaError_t launch_mulrem_fresh_b32(const uint64_t *A, const uint64_t *B, uint64_t *O, uint64_t pairs, const uint32_t *Tg,
@@ -34,8 +35,9 @@ static long g_mul_thread_min = -1; // minimum (values x chunks) for the thread-p
 static long g_mul_thread_chunk = 32; // 24 = the first thread-per-chunk kernel (3-way Karatsuba chunks)
 static long g_mul_circuit_seq = 0;
 static long g_adder_chain = getenv("HM_ADDER_CHAIN") ? atol(getenv("HM_ADDER_CHAIN")) : 4;   // 0 = round-1 thread kernels; else 10 * (window in smem) + CTAs per SM
-static long g_adder_phases = getenv("HM_ADDER_PHASES") ? atol(getenv("HM_ADDER_PHASES")) : 4; // work units per value of the scheduled adder chain
+static long g_adder_phases = getenv("HM_ADDER_PHASES") ? atol(getenv("HM_ADDER_PHASES")) : 0; // work units per value of the scheduled adder chain; 0 = by batch size
 static long g_host_chunk_mb = getenv("HM_HOST_CHUNK_MB") ? atol(getenv("HM_HOST_CHUNK_MB")) : 96; // per-stage bytes of the host-buffer pipeline
+static long g_pool_max_mb = getenv("HM_POOL_MAX_MB") ? atol(getenv("HM_POOL_MAX_MB")) : 16384; // larger batches use plain cudaMalloc
 static long g_adder_generic_seq = 0; // 1 = the generic adder evaluates the reference's formula literally (two long products per bit)  // 1 = launch the multiplier circuit's carry products one by one (the first plan)
 
 using hmk::Layout;
@@ -228,7 +230,7 @@ int alloc_batch(hm_context *ctx, hm_batch *b) {
     // Stream-ordered pool for ordinary batches (no device-wide sync, blocks are recycled).  Multi-GB results go through
     // plain cudaMalloc: returning such a block to the pool costs ~0.5 s of unmapping at the next synchronisation.
     cudaError_t e;
-    if (bytes <= ((size_t)1 << 30)) {
+    if (bytes <= ((size_t)(g_pool_max_mb > 0 ? g_pool_max_mb : 0) << 20)) {
         e = pool_alloc(ctx, &b->d, bytes);
         b->pooled = true;
     } else {
@@ -663,12 +665,20 @@ int hm_context_create(uint16_t d, uint16_t dp, uint16_t delta, uint16_t tau, int
         props.handleTypes = cudaMemHandleTypeNone;
         props.location.type = cudaMemLocationTypeDevice;
         props.location.id = device;
-        if (cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess && ctx->pool) {
+        static const int private_pool = getenv("HM_PRIVATE_POOL") ? atoi(getenv("HM_PRIVATE_POOL")) : 1; // 0 = round-1 behaviour (A/B only)
+        if (private_pool && cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess && ctx->pool) {
             uint64_t keep = UINT64_MAX;
             cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
         } else {
-            ctx->pool = nullptr; // fall back to the default pool, untouched
+            ctx->pool = nullptr; // the device's default pool
             cudaGetLastError();
+            if (!private_pool) {
+                cudaMemPool_t dpool = nullptr;
+                if (cudaDeviceGetDefaultMemPool(&dpool, device) == cudaSuccess && dpool) {
+                    uint64_t keep = UINT64_MAX;
+                    cudaMemPoolSetAttribute(dpool, cudaMemPoolAttrReleaseThreshold, &keep);
+                }
+            }
         }
     }
     cudaDeviceProp prop;
@@ -757,8 +767,13 @@ int hm_set_tuning(const char *key, long value) {
         return HM_OK;
     }
     if (strcmp(key, "adder_phases") == 0) {
-        if (value < 1 || value > (long)hmk::ADDER_MAX_PHASES) return HM_ERR_INVALID_ARGUMENT;
+        if (value < 0 || value > (long)hmk::ADDER_MAX_PHASES) return HM_ERR_INVALID_ARGUMENT;
         g_adder_phases = value;
+        return HM_OK;
+    }
+    if (strcmp(key, "pool_max_mb") == 0) {
+        if (value < 0 || value > (1 << 20)) return HM_ERR_INVALID_ARGUMENT;
+        g_pool_max_mb = value;
         return HM_OK;
     }
     if (strcmp(key, "host_chunk_mb") == 0) {
@@ -1301,30 +1316,45 @@ static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint
     return HM_OK;
 }
 
-int hm_encrypt(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, const uint8_t *masks, hm_batch **out) {
-    if (!ctx || !out || ((!values || !masks) && n)) return HM_ERR_INVALID_ARGUMENT;
+// Host plaintexts (and, unless seeded, host masks) -> device batch.  masks == NULL means: generate them on the device from
+// `seed`, bit-ciphertext u of this call taking position first_unit + u of the Philox stream.  With sync == false the call
+// returns as soon as the work is enqueued: the host buffers must stay valid until the context is synchronised.
+static int masks_generate_device_at(hm_context *ctx, size_t units, uint64_t seed, uint64_t first_unit, uint8_t *d_masks_out);
+static int encrypt_host_impl(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, const uint8_t *masks, uint64_t seed, uint64_t first_unit,
+                             bool sync, hm_batch **out) {
+    if (!ctx || !out || (!values && n)) return HM_ERR_INVALID_ARGUMENT;
     if (!ctx->has_pk) return HM_ERR_PUBLIC_KEY_UNSET;
     if (L == 0 || L % 8 != 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
     USE_DEV(ctx);
     const size_t vbytes = n * (L / 8), mbytes = n * L * ((ctx->tau + 7u) / 8u);
-    uint8_t *dv = nullptr, *dm = nullptr;
-    CK(pool_alloc(ctx, &dv, std::max<size_t>(vbytes, 16)));
-    cudaError_t e = pool_alloc(ctx, &dm, std::max<size_t>(mbytes, 16));
-    if (e != cudaSuccess) {
-        cudaFreeAsync(dv, ctx->stream);
-        return fail_cuda(ctx, e, "cudaMalloc(masks)");
+    PoolGuard dv(ctx), dm(ctx);
+    CK(pool_alloc(ctx, &dv.p, std::max<size_t>(vbytes, 16)));
+    CK(pool_alloc(ctx, &dm.p, std::max<size_t>(mbytes, 16)));
+    if (n) {
+        CK(cudaMemcpyAsync(dv.p, values, vbytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (masks) CK(cudaMemcpyAsync(dm.p, masks, mbytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     int rc = HM_OK;
-    if (n) {
-        e = cudaMemcpyAsync(dv, values, vbytes, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(dm, masks, mbytes, cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) rc = fail_cuda(ctx, e, "upload values/masks");
+    if (!masks) rc = masks_generate_device_at(ctx, n * L, seed, first_unit, static_cast<uint8_t *>(dm.p));
+    if (rc == HM_OK) rc = hm_encrypt_device(ctx, static_cast<const uint8_t *>(dv.p), n, L, static_cast<const uint8_t *>(dm.p), out);
+    if (sync) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream); // the caller's host buffers may be reused after return
+        if (rc == HM_OK && e != cudaSuccess) {
+            hm_batch_free(ctx, *out);
+            *out = nullptr;
+            rc = fail_cuda(ctx, e, "encrypt");
+        }
     }
-    if (rc == HM_OK) rc = hm_encrypt_device(ctx, dv, n, L, dm, out);
-    cudaFreeAsync(dv, ctx->stream);
-    cudaFreeAsync(dm, ctx->stream);
-    cudaStreamSynchronize(ctx->stream); // the caller's host buffers may be reused after return
     return rc;
+}
+
+int hm_encrypt(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, const uint8_t *masks, hm_batch **out) {
+    if (!masks && n) return HM_ERR_INVALID_ARGUMENT;
+    return encrypt_host_impl(ctx, values, n, L, masks ? masks : reinterpret_cast<const uint8_t *>(""), 0, 0, true, out);
+}
+int hm_encrypt_async(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, const uint8_t *masks, hm_batch **out) {
+    if (!masks && n) return HM_ERR_INVALID_ARGUMENT;
+    return encrypt_host_impl(ctx, values, n, L, masks ? masks : reinterpret_cast<const uint8_t *>(""), 0, 0, false, out);
 }
 
 // ---- seeded subset masks (Philox4x32-10) -----------------------------------------------------------
@@ -1341,41 +1371,26 @@ int hm_masks_generate_host(uint16_t tau, size_t units, uint64_t seed, uint8_t *m
     return HM_OK;
 }
 
-int hm_masks_generate_device(hm_context *ctx, size_t units, uint64_t seed, uint8_t *d_masks_out) {
+static int masks_generate_device_at(hm_context *ctx, size_t units, uint64_t seed, uint64_t first_unit, uint8_t *d_masks_out) {
     if (!ctx || (!d_masks_out && units)) return HM_ERR_INVALID_ARGUMENT;
     USE_DEV(ctx);
     if (!units) return HM_OK;
     const uint32_t mb = (ctx->tau + 7u) / 8u;
     const int grid = grid_for(ctx, (uint64_t)units * ((mb + 15) / 16), 256, 16);
-    hmk::mask_fill_kernel<<<grid, 256, 0, ctx->stream>>>(d_masks_out, units, mb, seed);
+    hmk::mask_fill_kernel<<<grid, 256, 0, ctx->stream>>>(d_masks_out, units, mb, seed, first_unit);
     LAUNCHED("mask_fill_kernel");
     return HM_OK;
 }
+int hm_masks_generate_device(hm_context *ctx, size_t units, uint64_t seed, uint8_t *d_masks_out) {
+    return masks_generate_device_at(ctx, units, seed, 0, d_masks_out);
+}
 
 int hm_encrypt_seeded(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, uint64_t seed, hm_batch **out) {
-    if (!ctx || !out || (!values && n)) return HM_ERR_INVALID_ARGUMENT;
-    if (!ctx->has_pk) return HM_ERR_PUBLIC_KEY_UNSET;
-    if (L == 0 || L % 8 != 0 || L > (uint32_t)hmk::MAX_SLOTS) return HM_ERR_INVALID_ARGUMENT;
-    USE_DEV(ctx);
-    const size_t vbytes = n * (L / 8), mbytes = n * L * ((ctx->tau + 7u) / 8u);
-    uint8_t *dv = nullptr, *dm = nullptr;
-    CK(pool_alloc(ctx, &dv, std::max<size_t>(vbytes, 16)));
-    cudaError_t e = pool_alloc(ctx, &dm, std::max<size_t>(mbytes, 16));
-    if (e != cudaSuccess) {
-        cudaFreeAsync(dv, ctx->stream);
-        return fail_cuda(ctx, e, "cudaMalloc(masks)");
-    }
-    int rc = HM_OK;
-    if (n) {
-        e = cudaMemcpyAsync(dv, values, vbytes, cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) rc = fail_cuda(ctx, e, "upload values");
-    }
-    if (rc == HM_OK) rc = hm_masks_generate_device(ctx, n * L, seed, dm);
-    if (rc == HM_OK) rc = hm_encrypt_device(ctx, dv, n, L, dm, out);
-    cudaFreeAsync(dv, ctx->stream);
-    cudaFreeAsync(dm, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-    return rc;
+    return encrypt_host_impl(ctx, values, n, L, nullptr, seed, 0, true, out);
+}
+int hm_encrypt_seeded_at(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, uint64_t seed, uint64_t first_unit, int sync,
+                         hm_batch **out) {
+    return encrypt_host_impl(ctx, values, n, L, nullptr, seed, first_unit, sync != 0, out);
 }
 
 int hm_decrypt_device(hm_context *ctx, const hm_batch *b, uint8_t *d_values_out) {
@@ -1435,24 +1450,27 @@ int hm_decrypt_device(hm_context *ctx, const hm_batch *b, uint8_t *d_values_out)
     return HM_OK;
 }
 
-int hm_decrypt(hm_context *ctx, const hm_batch *b, uint8_t *values_out) {
+static int decrypt_host_impl(hm_context *ctx, const hm_batch *b, uint8_t *values_out, bool sync) {
     if (!ctx || !b || (!values_out && b->n)) return HM_ERR_INVALID_ARGUMENT;
     if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;
     if (b->L % 8 != 0) return HM_ERR_INVALID_LENGTH;
     USE_DEV(ctx);
     const size_t bytes = b->n * (b->L / 8);
-    uint8_t *dout = nullptr;
-    CK(pool_alloc(ctx, &dout, std::max<size_t>(bytes, 16)));
-    int rc = hm_decrypt_device(ctx, b, dout);
+    PoolGuard dout(ctx);
+    CK(pool_alloc(ctx, &dout.p, std::max<size_t>(bytes, 16)));
+    int rc = hm_decrypt_device(ctx, b, static_cast<uint8_t *>(dout.p));
     if (rc == HM_OK && bytes) {
-        cudaError_t e = cudaMemcpyAsync(values_out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(values_out, dout.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
         if (e != cudaSuccess) rc = fail_cuda(ctx, e, "download plaintext");
     }
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (rc == HM_OK && e != cudaSuccess) rc = fail_cuda(ctx, e, "decrypt sync");
-    cudaFreeAsync(dout, ctx->stream);
+    if (sync) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (rc == HM_OK && e != cudaSuccess) rc = fail_cuda(ctx, e, "decrypt sync");
+    }
     return rc;
 }
+int hm_decrypt(hm_context *ctx, const hm_batch *b, uint8_t *values_out) { return decrypt_host_impl(ctx, b, values_out, true); }
+int hm_decrypt_async(hm_context *ctx, const hm_batch *b, uint8_t *values_out) { return decrypt_host_impl(ctx, b, values_out, false); }
 
 // ---- homomorphic operations -------------------------------------------------------------------
 int hm_op_min_d_over_delta(int op) { // reference src/impls/numbers.rs:27-50
@@ -2109,7 +2127,12 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                     sc.counter = ctx->d_sched;
                     sc.done = ctx->d_sched + 1;
                     sc.ngroups = (uint32_t)((n + 31) / 32);
-                    hmk::adder_chain_plan(a->L, wd, (uint32_t)std::max(1, phases), &sc);
+                    // Work units per value.  Splitting a value into phases pays when the batch is several waves of resident warps with a
+                    // ragged last wave (2^18 values = 3.46 waves: 4.44 -> 4.51 M adds/s with 8 phases); on one or two exact waves the
+                    // hand-over between warps only costs (75 776 values: 17.7 ms with 1 phase, 21.4 ms with 8).
+                    const uint64_t resident_warps = (uint64_t)ctx->sm_count * (chain % 10) * 4;
+                    const int auto_phases = (uint64_t)sc.ngroups * 2 >= resident_warps * 5 ? 8 : 1;
+                    hmk::adder_chain_plan(a->L, wd, (uint32_t)(phases > 0 ? phases : auto_phases), &sc);
                     CK(hmk::launch_adder_chain(wd, chain, a->d, b->d, o->d, n, a->L, make_layout(o), sc, ctx->sm_count, ctx->stream));
                     rc = post_launch(ctx, "adder_chain_kernel");
                     break;
@@ -2623,6 +2646,22 @@ int hm_measure_kara8_peak(hm_context *ctx, double *products_per_s) {
     cudaEventDestroy(e1);
     cudaFree(sink);
     *products_per_s = best;
+    return HM_OK;
+}
+
+int hm_measure_pipe_peaks(hm_context *ctx, double min_ms, double *out12) {
+    if (!ctx || !out12 || !(min_ms > 0)) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    hmk::PipeProbe p[3];
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(hmk::measure_pipe_peaks(ctx->sm_count, ctx->stream, min_ms, p));
+    for (int i = 0; i < 3; ++i) {
+        out12[4 * i + 0] = p[i].warp_instr_per_s;
+        out12[4 * i + 1] = p[i].ms;
+        out12[4 * i + 2] = (double)p[i].warps_per_sm;
+        out12[4 * i + 3] = p[i].cycle_counter_mhz;
+    }
+    ctx->launches += 12;
     return HM_OK;
 }
 

@@ -105,14 +105,15 @@ __host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 static __global__ void __launch_bounds__(256) mask_fill_kernel(uint8_t *__restrict__ masks, uint64_t units, uint32_t mask_bytes,
-                                                               uint64_t seed) {
+                                                               uint64_t seed, uint64_t first_unit) {
     const uint32_t blocks = (mask_bytes + 15) / 16;
     const uint64_t total = units * blocks;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t u = i / blocks;
         const uint32_t b = (uint32_t)(i % blocks);
+        const uint64_t gu = first_unit + u; // position in the stream: shards of one logical batch continue each other
         uint32_t r[4];
-        philox4x32_10((uint32_t)u, (uint32_t)(u >> 32), b, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        philox4x32_10((uint32_t)gu, (uint32_t)(gu >> 32), b, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
         uint8_t *dst = masks + u * mask_bytes + 16ull * b;
         const uint32_t nb = (mask_bytes - 16 * b < 16) ? (mask_bytes - 16 * b) : 16;
         if (nb == 16 && (mask_bytes % 16) == 0) {

@@ -37,6 +37,8 @@ extern "C" {
 
 typedef struct hm_context hm_context; /* Context            — src/context.rs:301-305 */
 typedef struct hm_batch hm_batch;     /* Vec<Ciphered<T>>   — src/cipher.rs:126-130, device resident */
+typedef struct hm_group hm_group;             /* one Context replicated on several GPUs of a box            */
+typedef struct hm_group_batch hm_group_batch; /* one logical batch, contiguous index shards on the devices  */
 
 typedef enum hm_status {
     HM_OK = 0,
@@ -92,8 +94,9 @@ int hm_context_device(const hm_context *ctx);
  * (two long products per bit) instead of the regrouped one-product-per-bit form; "mul_thread_chunk": 24 | 32 words per
  * chunk of the thread-per-chunk product kernel; "adder_chain": 0 = the round-1 thread-per-value adder kernels, otherwise
  * the dynamically scheduled chain of kernels_adder.cu as 10 * (window in shared memory) + CTAs per SM (4 = default, 3, 12, 13);
- * "adder_phases": work units per value of that chain (1..8); "host_chunk_mb": bytes per stage of the host-buffer pipeline
- * of hm_apply2_host (MiB, default 96).
+ * "adder_phases": work units per value of that chain (1..8; 0 = default: 8 for batches of at least 2.5 waves of resident warps, else 1); "host_chunk_mb": bytes per stage of the host-buffer pipeline
+ * of hm_apply2_host (MiB, default 96); "pool_max_mb": batches up to this size come from the context's stream-ordered pool,
+ * larger ones from plain cudaMalloc (MiB, default 16384).
  * All of them give the same polynomials: they are the A/B arms of tests. */
 int hm_set_tuning(const char *key, long value);
 
@@ -196,6 +199,16 @@ int hm_encrypt_device_into(hm_context *ctx, const uint8_t *d_values, size_t n, u
 int hm_masks_generate_host(uint16_t tau, size_t units, uint64_t seed, uint8_t *masks_out);
 int hm_masks_generate_device(hm_context *ctx, size_t units, uint64_t seed, uint8_t *d_masks_out);
 int hm_encrypt_seeded(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, uint64_t seed, hm_batch **out);
+/* The same for a shard of a larger logical batch: bit-ciphertext u of this call takes position first_unit + u of the mask
+ * stream (first_unit = first value of the shard x L), so shards encrypted separately equal the batch encrypted at once.
+ * sync == 0 returns once the work is enqueued (see the *_async calls). */
+int hm_encrypt_seeded_at(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, uint64_t seed, uint64_t first_unit, int sync,
+                         hm_batch **out);
+/* Asynchronous forms of hm_encrypt / hm_decrypt: they return as soon as the copies and kernels are enqueued on the
+ * context's stream.  The host buffers must stay valid (and, for decrypt, unread) until hm_context_synchronize; pinned
+ * memory (hm_host_alloc) keeps the copies asynchronous.  They let one host thread drive several devices at once. */
+int hm_encrypt_async(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, const uint8_t *masks, hm_batch **out);
+int hm_decrypt_async(hm_context *ctx, const hm_batch *b, uint8_t *values_out);
 /* Context::decrypt -> Ciphered::try_decipher -> CipheredBit::decipher — src/context.rs:480-488,
  * src/cipher.rs:217-250, :119-122.  Writes n * (L/8) bytes.  L % 8 != 0 -> HM_ERR_INVALID_LENGTH. */
 int hm_decrypt(hm_context *ctx, const hm_batch *b, uint8_t *values_out);
@@ -239,6 +252,34 @@ int hm_apply2_host_bounded(hm_context *ctx, int op, size_t n, uint32_t L, const 
 int hm_apply2_host(hm_context *ctx, int op, size_t n, uint32_t L, const uint32_t *a_words, const uint64_t *a_host,
                    const uint32_t *b_words, const uint64_t *b_host, uint64_t *out_host);
 
+/* ---- Device groups: one logical batch over several GPUs ------------------------------------------------------
+ * Ciphertexts are independent (src/cipher.rs:180-185, :227-237; the circuits of common.rs touch only their two operands),
+ * so a batch shards by value index with NO exchange step: hm_group_create replicates the parameters on `n_dev` devices
+ * (device_ids may repeat a device: two contexts on one GPU — useful for tests), hm_group_set_*_key replicate the keys and
+ * their derived tables, hm_group_encrypt / _apply2 / _apply1 / _decrypt split [0, n) into contiguous ranges (hm_shard_range:
+ * sizes differ by at most one, rank order = index order), enqueue every device's share from the calling thread and only then
+ * synchronise, and hm_group_decrypt gathers the plaintexts in index order.  Results are word for word those of one device.
+ * The per-device contexts and batch parts are reachable (hm_group_context, hm_group_batch_part) for anything not wrapped. */
+int hm_shard_range(size_t n, int rank, int world, size_t *first, size_t *count);
+int hm_group_create(uint16_t d, uint16_t dp, uint16_t delta, uint16_t tau, const int *device_ids, int n_dev, hm_group **out);
+void hm_group_destroy(hm_group *g);
+int hm_group_size(const hm_group *g);
+hm_context *hm_group_context(const hm_group *g, int i);
+int hm_group_set_secret_key(hm_group *g, const uint8_t *bytes, size_t len);
+int hm_group_set_public_key(hm_group *g, const uint8_t *const *polys, const size_t *lens, size_t n_polys);
+int hm_group_synchronize(hm_group *g);
+int hm_group_encrypt(hm_group *g, const uint8_t *values, size_t n, uint32_t L, const uint8_t *masks, hm_group_batch **out);
+int hm_group_encrypt_seeded(hm_group *g, const uint8_t *values, size_t n, uint32_t L, uint64_t seed, hm_group_batch **out);
+int hm_group_apply2(hm_group *g, int op, const hm_group_batch *a, const hm_group_batch *b, hm_group_batch **out);
+int hm_group_apply2_into(hm_group *g, int op, const hm_group_batch *a, const hm_group_batch *b, hm_group_batch *out);
+int hm_group_apply1(hm_group *g, int op, hm_group_batch *a);
+int hm_group_decrypt(hm_group *g, const hm_group_batch *b, uint8_t *values_out);
+int hm_group_batch_download(hm_group *g, const hm_group_batch *b, uint64_t *host);
+size_t hm_group_batch_len(const hm_group_batch *b);
+uint32_t hm_group_batch_bits(const hm_group_batch *b);
+hm_batch *hm_group_batch_part(const hm_group_batch *b, int i);
+void hm_group_batch_free(hm_group_batch *b);
+
 /* ---- Raw polynomial batches (L = 1) -------------------------------------------------------
  * Polynomial::add / mul / rem over batches — src/polynomial.rs:190-213, :252-310, :316-365.
  * rem is by the context's secret key S (the only divisor on the hot path, src/cipher.rs:120);
@@ -262,6 +303,14 @@ int hm_measure_alu_peak(hm_context *ctx, double *lop3_lane_ops_per_s, double *sm
  * device: the measured ceiling of the kernels that are chains of such products (thread-per-value adder: 2 881 per
  * u32 add; fused mul+rem at d=d'=128: 1 per pair, plus the fold). */
 int hm_measure_kara8_peak(hm_context *ctx, double *products_per_s);
+
+/* Hardware pipe peaks for the integer rooflines, measured on the context's device.  Three probes, each >= min_ms long
+ * (use >= 100 so that the SM clock has ramped; fastest of three launches), 8 independent chains per thread, every CTA resident:
+ *   0: IMAD.WIDE.U32 with both operands in per-thread registers (the 32x32->64 products of the carry-less leaf),
+ *   1: LOP3 on three registers,   2: the kernels' own mix, 1 IMAD.WIDE : 2 LOP3.
+ * out12[4 i ..] = { warp-instructions per second (whole device, CUDA-event time), duration in ms, resident warps per SM,
+ * clock64() ticks per microsecond (diagnostic only: on B200 that counter runs below the SM clock, sample nvidia-smi) }. */
+int hm_measure_pipe_peaks(hm_context *ctx, double min_ms, double *out12);
 
 /* ---- Host-side helpers (no GPU needed) ---------------------------------------------------- */
 /* Worst-case slot widths of a freshly encrypted value: (d+dp)/64+1 words per slot. */

@@ -215,3 +215,25 @@ def test_result_slot_bounds_follow_the_reference_degrees():
     assert bounds(N.HM_OP_MUL, [D] * 32, [D] * 32)[0] == N.HM_ERR_UNSUPPORTED  # u32 multiplication: infeasible growth
     assert bounds(N.HM_OP_NOT, [D], [D])[0] == N.HM_ERR_INVALID_ARGUMENT
     assert bounds(N.HM_OP_ADD, [1 << 40], [1])[0] == N.HM_ERR_INVALID_ARGUMENT
+
+
+def test_shard_range_matches_the_python_rule():
+    """hm_shard_range (C ABI, used by the device groups) == sharding.shard_range (used under torchrun): contiguous ranges in
+    rank order whose sizes differ by at most one."""
+    from homomorph_rust_b200.sharding import shard_range
+
+    lib = hm.lib()
+    for n in (0, 1, 7, 8, 9, 100, 262144, 262145):
+        for world in (1, 2, 3, 4, 8):
+            end = 0
+            for r in range(world):
+                f, c = C.c_size_t(), C.c_size_t()
+                assert lib.hm_shard_range(n, r, world, C.byref(f), C.byref(c)) == 0
+                assert (f.value, f.value + c.value) == shard_range(n, r, world)
+                assert f.value == end
+                end += c.value
+            assert end == n
+    f, c = C.c_size_t(), C.c_size_t()
+    assert lib.hm_shard_range(10, 2, 2, C.byref(f), C.byref(c)) == N.HM_ERR_INVALID_ARGUMENT
+    assert lib.hm_shard_range(10, 0, 0, C.byref(f), C.byref(c)) == N.HM_ERR_INVALID_ARGUMENT
+    assert lib.hm_group_size(None) == 0 and lib.hm_group_create(128, 128, 1, 128, None, 0, None) == N.HM_ERR_INVALID_ARGUMENT

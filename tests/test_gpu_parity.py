@@ -711,7 +711,7 @@ def test_add_chain_kernel_variants(oracle, hm, params, dtype, n, chain, phases):
     finally:
         lib.hm_set_tuning(b"adder_thread_min", -1)
         lib.hm_set_tuning(b"adder_chain", 4)
-        lib.hm_set_tuning(b"adder_phases", 4)
+        lib.hm_set_tuning(b"adder_phases", 0)
     np.testing.assert_array_equal(got, r_warp.to_host())
     k = min(n, 40)
     mbytes = (tau + 7) // 8
@@ -833,3 +833,64 @@ def test_upload_canonical_round_trip_and_orphans(oracle, hm):
     ctx.close()
     for batch in (ca, cb, s, back, tight, z):
         batch.free()
+
+
+@pytest.mark.parametrize("n_dev", [2, 3])
+def test_device_group_equals_one_device(oracle, hm, n_dev):
+    """hm_group_*: one logical batch sharded by value index over several contexts (distinct GPUs when the box has them,
+    else several contexts on GPU 0) gives word for word what one device gives — host masks and seeded masks, ADD / AND /
+    XOR / NOT, decrypt gathered in index order; ragged split (n not divisible by the group size)."""
+    import ctypes as C
+
+    from homomorph_rust_b200 import _native as N
+    from homomorph_rust_b200.api import ContextGroup
+
+    lib = hm.lib()
+    have = lib.hm_device_count()
+    devices = [i % have for i in range(n_dev)]
+    rng = np.random.default_rng(100 + n_dev)
+    sk, pk, skb, pkb = keys(oracle, *CONFIG_A, 47)
+    ctx = engine_context(hm, *CONFIG_A, skb, pkb)
+    grp = ContextGroup(hm.Parameters(*CONFIG_A), devices)
+    assert len(grp) == n_dev
+    grp.set_secret_key(hm.SecretKey.from_bytes(skb))
+    grp.set_public_key(hm.PublicKey.from_bytes(pkb))
+    n, L = 101, 32
+    a = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    b = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    ma, mb = masks_for(rng, n, L, 128), masks_for(rng, n, L, 128)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, seed=99)
+    ga, gb = grp.encrypt(a, ma), grp.encrypt(b, seed=99)
+    sizes = [ga.part_len(i) for i in range(n_dev)]
+    assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+    np.testing.assert_array_equal(ga.to_host(), ca.to_host())
+    np.testing.assert_array_equal(gb.to_host(), cb.to_host())  # shard r continues the Philox stream where shard r-1 stopped
+    for op in (hm.HomomorphicAddition, hm.HomomorphicAndGate, hm.HomomorphicXorGate, hm.HomomorphicOrGate):
+        one = ctx.apply2(op, ca, cb)
+        many = grp.apply2(op, ga, gb)
+        np.testing.assert_array_equal(many.to_host(), one.to_host())
+        np.testing.assert_array_equal(grp.decrypt(many), ctx.decrypt(one))
+        if op is hm.HomomorphicAddition:
+            np.testing.assert_array_equal(grp.decrypt(many), a + b)
+            want, _ = oracle.apply(oracle.OP_ADD, oracle_encrypt(oracle, pk, a[:6], ma[: 6 * L * 16]),
+                                   oracle_encrypt(oracle, pk, b[:6], ctx.seeded_masks(n * L, 99)[: 6 * L * 16]), L, threads=oracle.max_threads())
+            np.testing.assert_array_equal(many.to_host()[:6], expected_padded(want, 6, many.slot_words()))
+        many.free(); one.free()
+    grp.apply1(hm.HomomorphicNotGate, ga)
+    ctx.apply1(hm.HomomorphicNotGate, ca)
+    np.testing.assert_array_equal(ga.to_host(), ca.to_host())
+    np.testing.assert_array_equal(grp.decrypt(ga), ~a)
+    # tiny batches: fewer values than devices leaves empty shards
+    tiny = grp.encrypt(a[:1], ma[: L * 16])
+    assert [tiny.part_len(i) for i in range(n_dev)] == [1] + [0] * (n_dev - 1)
+    np.testing.assert_array_equal(grp.decrypt(tiny), a[:1])
+    empty = grp.encrypt(a[:0], ma[:0])
+    assert grp.decrypt(empty).size == 0
+    # errors surface like on one context
+    g2 = ContextGroup(hm.Parameters(*CONFIG_A), devices[:1])
+    with pytest.raises(hm.PublicKeyUnset):
+        g2.encrypt(a, ma)
+    g2.close()
+    for x in (ga, gb, tiny, empty):
+        x.free()
+    grp.close()

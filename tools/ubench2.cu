@@ -34,13 +34,20 @@ enum Kind {
     FFMA_RRR,     // fma.rn.f32
     MIX_1W_1D,    // 1 mul.wide + 1 dfma (are the FP64 and integer-multiply pipes separate?)
     MIX_2L_1D,    // 2 lop3 + 1 dfma
+    MIX_2W_1L,    // 2 mul.wide + 1 lop3
+    MIX_1W_4L,    // 1 mul.wide + 4 lop3
+    MIX_1W_2LI,   // 1 mul.wide + 2 lop3 with an immediate operand each (fewer register reads)
+    MIX_1M_1L,    // 1 mul.lo + 1 lop3
+    MIX_1M_2L,    // 1 mul.lo + 2 lop3
+    MIX_1W_2L_2MOV, // 1 mul.wide + 2 lop3 + 2 register moves
+    MIX_1W_1L_1S, // 1 mul.wide + 1 lop3 + 1 shf
     KCOUNT
 };
 static const char *names[KCOUNT] = {"IMAD.WIDE r*r (32-bit values)", "IMAD.WIDE r*r+r64", "IMAD.WIDE r*r (16-bit values)", "IMAD.WIDE r*r (one 16-bit value)",
                                      "IMAD.WIDE r*uniform32", "IMAD.WIDE r*uniform14", "IMAD lo r*r", "IMAD.HI r*r", "LOP3 r,r,r", "LOP3 r,r,imm", "SHF r,r",
                                      "1 IMAD.WIDE + 2 LOP3", "1 IMAD.WIDE + 1 LOP3", "1 IMAD.WIDE + 3 LOP3", "DFMA", "DADD", "FFMA", "1 IMAD.WIDE + 1 DFMA",
-                                     "2 LOP3 + 1 DFMA"};
-static const int per_iter[KCOUNT] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3, 2, 4, 1, 1, 1, 2, 3};
+                                     "2 LOP3 + 1 DFMA", "2 IMAD.WIDE + 1 LOP3", "1 IMAD.WIDE + 4 LOP3", "1 IMAD.WIDE + 2 LOP3(imm)", "1 IMAD lo + 1 LOP3", "1 IMAD lo + 2 LOP3", "1 IMAD.WIDE + 2 LOP3 + 2 MOV", "1 IMAD.WIDE + 1 LOP3 + 1 SHF"};
+static const int per_iter[KCOUNT] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3, 2, 4, 1, 1, 1, 2, 3, 3, 5, 3, 2, 3, 5, 3};
 
 template <int K> __global__ void __launch_bounds__(256) probe(uint32_t *out, uint32_t seed, long long *clk, int iters, uint32_t ubig, uint32_t usmall) {
     uint32_t x[ILP], y[ILP], z[ILP];
@@ -78,7 +85,46 @@ template <int K> __global__ void __launch_bounds__(256) probe(uint32_t *out, uin
                 asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(x[i]), "r"(y[i]));
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"((uint32_t)w[i]), "r"((uint32_t)(w[i] >> 32)));
                 if (K != MIX_1W_1L) asm volatile("lop3.b32 %0, %0, %1, 0x11111111, 0x78;" : "+r"(x[i]) : "r"(z[i]));
+                else x[i] = z[i] | 1u; // folded into the lop3 above by the compiler or one more LOP3: see the SASS
                 if (K == MIX_1W_3L) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(z[i]), "r"(x[i]));
+            }
+            if (K == MIX_2W_1L) {
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(x[i]), "r"(y[i]));
+                uint64_t w2;
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w2) : "r"(z[i]), "r"(y[i]));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"((uint32_t)w[i]), "r"((uint32_t)(w2 >> 32)));
+                z[i] = (uint32_t)w2 | 1u;
+            }
+            if (K == MIX_1W_4L) {
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(x[i]), "r"(y[i]));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"((uint32_t)w[i]), "r"((uint32_t)(w[i] >> 32)));
+                asm volatile("lop3.b32 %0, %0, %1, 0x11111111, 0x78;" : "+r"(x[i]) : "r"(z[i]));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(z[i]), "r"(x[i]));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"(y[i]), "r"(x[i]));
+            }
+            if (K == MIX_1W_2LI) {
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(x[i]), "r"(y[i]));
+                asm volatile("lop3.b32 %0, %0, %1, 0x22222222, 0x78;" : "+r"(z[i]) : "r"((uint32_t)w[i]));
+                asm volatile("lop3.b32 %0, %0, %1, 0x11111111, 0x78;" : "+r"(x[i]) : "r"((uint32_t)(w[i] >> 32)));
+            }
+            if (K == MIX_1M_1L || K == MIX_1M_2L) {
+                asm volatile("mul.lo.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"(x[i]), "r"(y[i]));
+                if (K == MIX_1M_2L) asm volatile("lop3.b32 %0, %0, %1, 0x11111111, 0x78;" : "+r"(y[i]) : "r"(z[i]));
+            }
+            if (K == MIX_1W_2L_2MOV) {
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(x[i]), "r"(y[i]));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"((uint32_t)w[i]), "r"((uint32_t)(w[i] >> 32)));
+                asm volatile("lop3.b32 %0, %0, %1, 0x11111111, 0x78;" : "+r"(x[i]) : "r"(z[i]));
+                uint32_t m1, m2;
+                asm volatile("mov.b32 %0, %1;" : "=r"(m1) : "r"(x[i]));
+                asm volatile("mov.b32 %0, %1;" : "=r"(m2) : "r"(z[i]));
+                x[i] = m1; z[i] = m2;
+            }
+            if (K == MIX_1W_1L_1S) {
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(x[i]), "r"(y[i]));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(z[i]) : "r"((uint32_t)w[i]), "r"((uint32_t)(w[i] >> 32)));
+                asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(x[i]) : "r"(z[i]));
             }
             if (K == DFMA_RRR) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(e[i]), "d"(e[(i + 1) % ILP]));
             if (K == DADD_RR) asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(e[i]));
@@ -149,6 +195,9 @@ template <int THREADS, int MINB> void run_kara(int sms, uint32_t *out, double ta
 }
 
 template <int K> void run(int sms, int ctas_per_sm, uint32_t *out, long long *clk, double target_ms) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe<K>, 256, 0);
+    if (ctas_per_sm > occ) ctas_per_sm = occ; // every CTA resident, so a CTA's cycle count spans the kernel
     const int blocks = sms * ctas_per_sm, threads = 256;
     int iters = 1 << 14;
     float ms = 0;
@@ -188,7 +237,7 @@ int main(int argc, char **argv) {
 #define RUN(K) run<K>(sms, 4, out, clk, target_ms)
     RUN(MULW_RR); RUN(MADW_RRR); RUN(MULW_RR16); RUN(MULW_RR_A16); RUN(MULW_RU); RUN(MULW_RU16); RUN(MUL_LO); RUN(MUL_HI);
     RUN(LOP3_RRR); RUN(LOP3_RRI); RUN(SHF_RR); RUN(MIX_1W_2L); RUN(MIX_1W_1L); RUN(MIX_1W_3L); RUN(DFMA_RRR); RUN(DADD_RR); RUN(FFMA_RRR);
-    RUN(MIX_1W_1D); RUN(MIX_2L_1D);
+    RUN(MIX_1W_1D); RUN(MIX_2L_1D); RUN(MIX_2W_1L); RUN(MIX_1W_4L); RUN(MIX_1W_2LI); RUN(MIX_1M_1L); RUN(MIX_1M_2L); RUN(MIX_1W_2L_2MOV); RUN(MIX_1W_1L_1S);
     run<MULW_RR>(sms, 2, out, clk, target_ms);
     run<MIX_1W_2L>(sms, 2, out, clk, target_ms);
     run<MIX_1W_2L>(sms, 8, out, clk, target_ms);
