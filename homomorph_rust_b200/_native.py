@@ -72,6 +72,10 @@ def lib() -> C.CDLL:
         "hm_set_tuning": (C.c_int, [C.c_char_p, C.c_long]),
         "hm_set_secret_key": (C.c_int, [vp, vp, sz]),
         "hm_set_public_key": (C.c_int, [vp, C.POINTER(vp), C.POINTER(sz), sz]),
+        "hm_generate_keys_seeded": (C.c_int, [vp, C.c_uint64]),
+        "hm_key_stream_host": (C.c_int, [C.c_uint64, C.c_uint32, sz, vp]),
+        "hm_secret_key_bytes": (C.c_int, [vp, vp, sz, C.POINTER(sz)]),
+        "hm_public_key_bytes": (C.c_int, [vp, sz, vp, sz, C.POINTER(sz)]),
         "hm_has_secret_key": (C.c_int, [vp]),
         "hm_has_public_key": (C.c_int, [vp]),
         "hm_batch_len": (sz, [vp]),

@@ -379,6 +379,23 @@ class Context:
         p = self._params
         self.set_public_key(PublicKey.random(p.dp(), p.delta(), p.tau(), self._sk, rng))
 
+    def generate_keys_seeded(self, seed: int) -> None:
+        """Both keys from a 64-bit seed, the public polynomials computed on the GPU (hm_generate_keys_seeded).  Reproducible
+        by the reference fed with hm_key_stream_host's bytes; for tests and benchmarks, not for production keys."""
+        _check(self._h, N.lib().hm_generate_keys_seeded(self._h, seed))
+        ln = C.c_size_t()
+        _check(self._h, N.lib().hm_secret_key_bytes(self._h, None, 0, C.byref(ln)))
+        buf = (C.c_uint8 * ln.value)()
+        _check(self._h, N.lib().hm_secret_key_bytes(self._h, buf, ln.value, C.byref(ln)))
+        self._sk = SecretKey.from_bytes(bytes(buf))
+        rows = []
+        for i in range(self._params.tau()):
+            _check(self._h, N.lib().hm_public_key_bytes(self._h, i, None, 0, C.byref(ln)))
+            b = (C.c_uint8 * ln.value)()
+            _check(self._h, N.lib().hm_public_key_bytes(self._h, i, b, ln.value, C.byref(ln)))
+            rows.append(bytes(b))
+        self._pk = PublicKey.from_bytes(rows)
+
     def get_secret_key(self) -> Optional[SecretKey]:
         return self._sk
 

@@ -84,6 +84,7 @@ struct hm_context {
 
     // public key and what is derived from it
     bool has_pk = false;
+    std::vector<gf2::words> T_host; // the tau public polynomials as set (for hm_public_key_bytes)
     size_t fresh_deg = 0; // max degree over the T_i (== d+dp for generated keys)
     uint32_t wf = 0;      // u64 words of a fresh slot
     uint32_t enc_wb = 0, enc_groups = 0, enc_table_words = 0;
@@ -331,6 +332,7 @@ void clear_public(hm_context *ctx) {
     if (ctx->d_enc_table6) cudaFree(ctx->d_enc_table6);
     ctx->d_enc_table = nullptr;
     ctx->d_enc_table6 = nullptr;
+    ctx->T_host.clear();
     ctx->has_pk = false;
     ctx->enc_table_words = 0;
 }
@@ -850,6 +852,7 @@ int hm_set_public_key(hm_context *ctx, const uint8_t *const *polys, const size_t
         maxdeg = std::max(maxdeg, gf2::degree(T[i].data(), T[i].size()));
     }
     clear_public(ctx);
+    ctx->T_host = T;
     ctx->fresh_deg = maxdeg;
     ctx->wf = (uint32_t)(maxdeg / 64 + 1);
     const uint32_t wf = ctx->wf, tau = ctx->tau;
@@ -904,6 +907,92 @@ int hm_set_public_key(hm_context *ctx, const uint8_t *const *polys, const size_t
     ctx->enc_table_words = (uint32_t)tab.size();
     ctx->enc_table_in_smem = in_smem;
     ctx->has_pk = true;
+    return HM_OK;
+}
+
+// ---- seeded key generation on the device ----------------------------------------------------------
+int hm_key_stream_host(uint64_t seed, uint32_t stream, size_t nbytes, uint8_t *out) {
+    if (!out && nbytes) return HM_ERR_INVALID_ARGUMENT;
+    for (size_t b = 0; b < nbytes; ++b) out[b] = (uint8_t)(hmk::key_stream_word(seed, stream, b / 8) >> (8 * (b % 8)));
+    return HM_OK;
+}
+
+int hm_generate_keys_seeded(hm_context *ctx, uint64_t seed) {
+    if (!ctx) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    const uint32_t d = ctx->d, dp = ctx->dp, delta = ctx->delta, tau = ctx->tau;
+    // S = Polynomial::random(d) from stream 0 (src/context.rs:160-162, src/polynomial.rs:73-96).  It is needed on the host
+    // anyway: the decrypt vector and the fold tables are built there.
+    const uint32_t ws = d / 64 + 1;
+    std::vector<uint64_t> S(ws);
+    for (uint32_t j = 0; j < ws; ++j) S[j] = hmk::key_stream_word(seed, 0, j);
+    S[ws - 1] &= ((uint64_t)1 << (d % 64)) - 1;
+    S[ws - 1] |= (uint64_t)1 << (d % 64);
+    int rc = hm_set_secret_key(ctx, reinterpret_cast<const uint8_t *>(S.data()), (size_t)ws * 8);
+    if (rc != HM_OK) return rc;
+    // T_i = S * Q_i + X * R_i on the device (src/context.rs:249-261)
+    const uint32_t wq = dp / 64 + 1, wr = (delta + 1) / 64 + 1, wt = (d + dp) / 64 + 1;
+    PoolGuard gS(ctx), gQ(ctx), gR(ctx), gT(ctx);
+    CK(pool_alloc(ctx, &gS.p, (size_t)ws * 8));
+    CK(pool_alloc(ctx, &gQ.p, (size_t)tau * wq * 8));
+    CK(pool_alloc(ctx, &gR.p, (size_t)tau * wr * 8));
+    CK(pool_alloc(ctx, &gT.p, (size_t)tau * wt * 8));
+    CK(cudaMemcpyAsync(gS.p, S.data(), (size_t)ws * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(gT.p, 0, (size_t)tau * wt * 8, ctx->stream));
+    hmk::keygen_fill_kernel<<<tau, 128, 0, ctx->stream>>>(static_cast<uint64_t *>(gQ.p), static_cast<uint64_t *>(gR.p), tau, dp, delta, seed);
+    LAUNCHED("keygen_fill_kernel");
+    auto view = [](void *base, uint64_t stride, uint32_t w, uint64_t deg) {
+        View v;
+        v.base = static_cast<uint64_t *>(base);
+        v.stride = stride;
+        v.off = 0;
+        v.w = w;
+        v.deg = deg;
+        return v;
+    };
+    View vS = view(gS.p, 0, ws, d), vQ = view(gQ.p, wq, wq, dp), vR = view(gR.p, wr, wr, (uint64_t)delta + 1), vT = view(gT.p, wt, wt, (uint64_t)d + dp);
+    std::vector<MulOp> ops(1, MulOp{vS, vQ, vT}); // S is the same for every i: a view with stride 0
+    rc = launch_mul_ops(ctx, ops, tau, true);
+    if (rc != HM_OK) return rc;
+    View vTr = vT;
+    vTr.w = std::min(wt, wr);
+    rc = launch_xor_views(ctx, vTr, vTr, vR, tau); // + X * R_i over its own width (deg X R_i = delta + 1 <= d + dp)
+    if (rc != HM_OK) return rc;
+    std::vector<uint64_t> T((size_t)tau * wt);
+    CK(cudaMemcpyAsync(T.data(), gT.p, T.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::fill(S.begin(), S.end(), 0);
+    // PublicKey::to_bytes format: degree/64+1 little-endian words per polynomial (src/polynomial.rs:99-105)
+    std::vector<const uint8_t *> ptrs(tau);
+    std::vector<size_t> lens(tau);
+    for (uint32_t i = 0; i < tau; ++i) {
+        const uint64_t *w = &T[(size_t)i * wt];
+        ptrs[i] = reinterpret_cast<const uint8_t *>(w);
+        lens[i] = (gf2::degree(w, wt) / 64 + 1) * 8;
+    }
+    return hm_set_public_key(ctx, ptrs.data(), lens.data(), tau);
+}
+
+// SecretKey::to_bytes / PublicKey::to_bytes()[i] of the keys the context holds (src/context.rs:192-194, :291-297):
+// degree/64+1 little-endian u64 words.  *len = bytes needed; out may be NULL to query.
+int hm_secret_key_bytes(const hm_context *ctx, uint8_t *out, size_t capacity, size_t *len) {
+    if (!ctx || !len) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_sk) return HM_ERR_SECRET_KEY_UNSET;
+    *len = (ctx->ds / 64 + 1) * 8;
+    if (!out) return HM_OK;
+    if (capacity < *len) return HM_ERR_INVALID_ARGUMENT;
+    memcpy(out, ctx->S.data(), *len);
+    return HM_OK;
+}
+int hm_public_key_bytes(const hm_context *ctx, size_t i, uint8_t *out, size_t capacity, size_t *len) {
+    if (!ctx || !len) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_pk) return HM_ERR_PUBLIC_KEY_UNSET;
+    if (i >= ctx->T_host.size()) return HM_ERR_INVALID_ARGUMENT;
+    const gf2::words &t = ctx->T_host[i];
+    *len = (gf2::degree(t.data(), t.size()) / 64 + 1) * 8;
+    if (!out) return HM_OK;
+    if (capacity < *len) return HM_ERR_INVALID_ARGUMENT;
+    memcpy(out, t.data(), *len);
     return HM_OK;
 }
 

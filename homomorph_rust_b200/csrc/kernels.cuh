@@ -125,6 +125,50 @@ static __global__ void __launch_bounds__(256) mask_fill_kernel(uint8_t *__restri
 }
 
 // ----------------------------------------------------------------------------------------
+// Seeded key generation, reference src/context.rs:249-261: T_i = S * Q_i + X * R_i with Q_i, R_i drawn by
+// Polynomial::random (src/polynomial.rs:73-96: random bytes -> little-endian words, bits above the degree cleared, the
+// leading coefficient set).  The random bytes are a documented Philox4x32-10 stream (hm_key_stream_host computes the same):
+//   bytes [16 j, 16 j + 16) of stream s = Philox(counter = (j_lo, j_hi, s, "KEYS"), key = seed),  s = 0: S, s = 1: Q_0 R_0 Q_1 R_1 ...
+// keygen_fill_kernel lays out Q_i (wq words) and X * R_i (wr words) for every i; S * Q_i is one launch of the product kernels
+// with S broadcast (a view with stride 0) and the sum one XOR launch.
+// ----------------------------------------------------------------------------------------
+constexpr uint32_t KEY_STREAM_TAG = 0x5359454Bu; // "KEYS"
+__host__ __device__ inline uint64_t key_stream_word(uint64_t seed, uint32_t stream, uint64_t word_index) { // u64 word `word_index` of the byte stream
+    uint32_t r[4];
+    const uint64_t blk = word_index >> 1;
+    philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), stream, KEY_STREAM_TAG, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    return (word_index & 1) ? ((uint64_t)r[2] | ((uint64_t)r[3] << 32)) : ((uint64_t)r[0] | ((uint64_t)r[1] << 32));
+}
+static __global__ void __launch_bounds__(128) keygen_fill_kernel(uint64_t *__restrict__ Q, uint64_t *__restrict__ RX, uint32_t tau, uint32_t dp, uint32_t delta,
+                                                                 uint64_t seed) {
+    const uint32_t wq = dp / 64 + 1, wr0 = delta / 64 + 1, wr = (delta + 1) / 64 + 1; // words of Q_i, R_i, X * R_i
+    const uint32_t i = blockIdx.x;
+    if (i >= tau) return;
+    const uint64_t base = (uint64_t)i * (wq + wr0); // u64 word offset of (Q_i, R_i) in stream 1
+    for (uint32_t j = threadIdx.x; j < wq; j += blockDim.x) {
+        uint64_t w = key_stream_word(seed, 1, base + j);
+        if (j == wq - 1) { // src/polynomial.rs:89-90
+            w &= ((uint64_t)1 << (dp % 64)) - 1;
+            w |= (uint64_t)1 << (dp % 64);
+        }
+        Q[(size_t)i * wq + j] = w;
+    }
+    for (uint32_t j = threadIdx.x; j < wr; j += blockDim.x) { // (X * R_i)[j] = R_i[j] << 1 | R_i[j-1] >> 63
+        auto rword = [&](uint32_t t) -> uint64_t {
+            if (t >= wr0) return 0;
+            uint64_t w = key_stream_word(seed, 1, base + wq + t);
+            if (t == wr0 - 1) {
+                w &= ((uint64_t)1 << (delta % 64)) - 1;
+                w |= (uint64_t)1 << (delta % 64);
+            }
+            return w;
+        };
+        const uint64_t cur = rword(j), prev = j ? rword(j - 1) : 0;
+        RX[(size_t)i * wr + j] = (cur << 1) | (prev >> 63);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // K2  subset-XOR encryption                         reference src/cipher.rs:99-115
 //
 //   C = XOR_{i : mask bit i} T_i  XOR  x

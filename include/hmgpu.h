@@ -108,6 +108,19 @@ int hm_set_secret_key(hm_context *ctx, const uint8_t *bytes, size_t len);
 /* Context::set_public_key(PublicKey::from_bytes(..)) — src/context.rs:239-245, :592-595.
  * polys[i]/lens[i] = PublicKey::to_bytes()[i]; n_polys must equal tau. */
 int hm_set_public_key(hm_context *ctx, const uint8_t *const *polys, const size_t *lens, size_t n_polys);
+/* Context::generate_secret_key + generate_public_key (src/context.rs:421-454) from a 64-bit seed instead of getrandom:
+ * S = Polynomial::random(d) on the host, T_i = S * Q_i + X * R_i (src/context.rs:249-261) for all i on the device (one
+ * product launch with S broadcast + one XOR launch).  The random bytes are a documented Philox4x32-10 stream —
+ * hm_key_stream_host(seed, stream, ...) returns it: stream 0 feeds S, stream 1 feeds Q_0, R_0, Q_1, R_1, ... in the order
+ * and byte counts the reference draws them (Polynomial::random: (degree/64+1)*8 bytes each) — so the reference fed with the
+ * same bytes (a getrandom shim) holds the same keys.  REPRODUCIBILITY / TESTING ONLY: Philox is not a cryptographic
+ * generator and 64 bits of seed are not a key; production keys come from hm_set_secret_key / hm_set_public_key. */
+int hm_generate_keys_seeded(hm_context *ctx, uint64_t seed);
+int hm_key_stream_host(uint64_t seed, uint32_t stream, size_t nbytes, uint8_t *out);
+/* SecretKey::to_bytes() / PublicKey::to_bytes()[i] of the keys the context holds (src/context.rs:192-194, :291-297).
+ * *len receives the byte count; out == NULL only queries it. */
+int hm_secret_key_bytes(const hm_context *ctx, uint8_t *out, size_t capacity, size_t *len);
+int hm_public_key_bytes(const hm_context *ctx, size_t i, uint8_t *out, size_t capacity, size_t *len);
 int hm_has_secret_key(const hm_context *ctx);
 int hm_has_public_key(const hm_context *ctx);
 
@@ -191,7 +204,10 @@ int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32
 /* Same, writing into an existing batch of n values x L fresh-width slots (no allocation). */
 int hm_encrypt_device_into(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
                            hm_batch *out);
-/* Seeded subset masks (Philox4x32-10, Random123): bytes [16 b, 16 b + 16) of the mask of bit-ciphertext u are
+/* Seeded subset masks (Philox4x32-10, Random123) — REPRODUCIBILITY / TESTING ONLY: the masks are the only randomness behind
+ * ciphertext indistinguishability, the reference draws them from the OS (getrandom, src/cipher.rs:92-97) and Philox keyed
+ * by a 64-bit seed is not a cryptographic generator.  Production callers pass masks from a CSPRNG to hm_encrypt.
+ * Stream layout: bytes [16 b, 16 b + 16) of the mask of bit-ciphertext u are
  * Philox(counter = (u_lo, u_hi, b, 0), key = (seed_lo, seed_hi)), words little endian, truncated to ceil(tau/8) bytes.
  * The *_host variant computes the same stream on the CPU (no GPU needed), so a seeded encryption can be reproduced
  * bit for bit by the reference/oracle fed with these masks.  hm_encrypt_seeded = hm_encrypt with device-generated

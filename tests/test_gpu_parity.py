@@ -894,3 +894,43 @@ def test_device_group_equals_one_device(oracle, hm, n_dev):
     for x in (ga, gb, tiny, empty):
         x.free()
     grp.close()
+
+
+@pytest.mark.parametrize("params", [CONFIG_A, CONFIG_B, (64, 32, 8, 32), (6, 3, 2, 5), (200, 130, 63, 17)])
+def test_generate_keys_on_device(oracle, hm, params):
+    """hm_generate_keys_seeded: T_i = S * Q_i + X * R_i computed on the GPU equals the oracle's keygen (src/context.rs:249-261,
+    src/polynomial.rs:73-96) fed with the same documented byte stream; the keys then encrypt / decrypt correctly."""
+    import ctypes as C
+
+    d, dp, delta, tau = params
+    lib = hm.lib()
+    seed = 0xC0FFEE + d
+    ctx = hm.Context(hm.Parameters(*params))
+    ctx.generate_keys_seeded(seed)
+    nb = lambda deg: (deg // 64 + 1) * 8
+    rs = np.zeros(nb(d), dtype=np.uint8)
+    assert lib.hm_key_stream_host(seed, 0, rs.size, rs.ctypes.data) == 0
+    rp = np.zeros(tau * (nb(dp) + nb(delta)), dtype=np.uint8)
+    assert lib.hm_key_stream_host(seed, 1, rp.size, rp.ctypes.data) == 0
+    u8p = C.POINTER(C.c_uint8)
+    L = oracle.lib()
+    osk = oracle.PolyVec(L.orc_keygen_sk(d, rs.ctypes.data_as(u8p)))
+    opk = oracle.PolyVec(L.orc_keygen_pk(dp, delta, tau, osk._h, rp.ctypes.data_as(u8p)))
+    assert ctx.get_secret_key().to_bytes() == osk.words(0).astype("<u8").tobytes()
+    got = ctx.get_public_key().to_bytes()
+    assert len(got) == tau
+    for i in range(tau):
+        assert got[i] == opk.words(i).astype("<u8").tobytes(), f"T_{i} differs"
+        assert opk.degree(i) == d + dp  # exact degree: both leading coefficients are forced
+    rng = np.random.default_rng(3)
+    v = rng.integers(0, 256, size=50, dtype=np.uint8)
+    m = masks_for(rng, 50, 8, tau)
+    c = ctx.encrypt(v, m)
+    np.testing.assert_array_equal(c.to_host(), expected_padded(oracle_encrypt(oracle, opk, v, m), 50, c.slot_words()))
+    np.testing.assert_array_equal(ctx.decrypt(c), v)
+    # a different seed gives different keys; the stream is deterministic
+    ctx2 = hm.Context(hm.Parameters(*params))
+    ctx2.generate_keys_seeded(seed)
+    assert ctx2.get_public_key().to_bytes() == got
+    ctx2.generate_keys_seeded(seed + 1)
+    assert ctx2.get_public_key().to_bytes() != got
