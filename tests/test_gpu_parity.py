@@ -934,3 +934,28 @@ def test_generate_keys_on_device(oracle, hm, params):
     assert ctx2.get_public_key().to_bytes() == got
     ctx2.generate_keys_seeded(seed + 1)
     assert ctx2.get_public_key().to_bytes() != got
+
+
+def test_multiword_kat_on_the_engine(oracle, hm):
+    """The committed 3- and 5-word known-answer vectors (tests/golden/kat_multiword.json, minted by the big-integer model and
+    re-derived by numpy bit vectors in tests/test_oracle_model.py) through hm_poly_mul and hm_poly_rem."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_multiword.json")) as f:
+        cases = json.load(f)["cases"]
+    ctx = hm.Context(hm.Parameters(128, 128, 1, 128))
+    for c in cases:
+        a = np.array([[int(x, 16) for x in c["a"]]], dtype=np.uint64)
+        b = np.array([[int(x, 16) for x in c["b"]]], dtype=np.uint64)
+        want = np.array([int(x, 16) for x in c["out"]], dtype=np.uint64)
+        if c["kind"] == "mul":
+            ca, cb = ctx.upload(a, [a.shape[1]]), ctx.upload(b, [b.shape[1]])
+            got = ctx.poly_mul(ca, cb).to_host()[0]
+        else:
+            s = int("".join(reversed(c["b"])), 16)
+            if s.bit_length() - 1 < 1:
+                continue
+            ctx.set_secret_key(hm.SecretKey.from_bytes(b[0].astype("<u8").tobytes()))
+            got = ctx.poly_rem(ctx.upload(a, [a.shape[1]])).to_host()[0]
+        assert np.array_equal(got[: want.size], want) and not got[want.size :].any(), c
