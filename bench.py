@@ -46,18 +46,18 @@ BITMACS_PER_ADD = 2.751e8        # schoolbook AND-XOR pairs over the 93 referenc
 BYTES_PER_ADD = 2560 + 46912     # 2 x 32 x 5 words in, 5 864 words out
 BITMACS_PER_MULREM = 66049 + 49665
 BYTES_PER_MULREM = 96
-# Executed instructions of the dominant kernel, from the ncu capture of the shipped adder_chain_kernel<8,0,4>
-# (profiles/r02_adder_chain_ncu.txt: smsp__inst_executed_pipe_{fmaheavy,alu}.sum and dram__bytes_{read,write}.sum of a
-# 75 776-pair launch, divided by 75 776).  Warp-level instructions per add (one thread = one add, so / 32 of the thread count).
+# Executed instructions and DRAM traffic of the dominant kernel, from the ncu capture of the shipped adder_chain_kernel<8,0,4>
+# at the bench size (profiles/r02_adder_chain_ncu.txt: one launch over 2^18 pairs, 58.12 ms under ncu), divided by 2^18.
+# Warp-level instructions per add (one thread = one add, 32 adds per warp instruction).
 NCU = {
-    "source": "profiles/r02_adder_chain_ncu.txt (ncu --set full + pipe instruction counts, adder_chain_kernel<8,0,4>, 75 776 pairs)",
-    "fmaheavy_warp_instr_per_add": 3076519808 / 75776,   # smsp__inst_executed_pipe_fmaheavy.sum: 40 600 (2 881 products x 432 IMAD.WIDE / 32 = 38 894, + moves)
-    "alu_warp_instr_per_add": 5996560128 / 75776,        # smsp__inst_executed_pipe_alu.sum: 79 135 (LOP3 & co)
-    "all_warp_instr_per_add": 9405915411 / 75776,        # smsp__inst_executed.sum: 124 128
-    "dram_bytes_per_add": (4.104197e9 + 4.721930e9) / 75776,  # dram__bytes_read.sum + dram__bytes_write.sum: 116.5 KB
-    "pipe_pct_at_capture": {"alu": 47.27, "fmaheavy": 47.50, "adds_per_s_at_capture": 75776 / 21.408736e-3,
-                            "note": "sm__pipe_{alu,fmaheavy}_cycles_active.avg.pct_of_peak_sustained_elapsed of the single-wave capture (3.54 M adds/s): "
-                                    "ncu's 100 % is 2.0 (ALU) / 1.02 (IMAD.WIDE) warp-instructions per clock per SM; scale by adds/s for other rates"},
+    "source": "profiles/r02_adder_chain_ncu.txt (ncu --set full + pipe instruction counts, adder_chain_kernel<8,0,4>, 2^18 pairs, one launch)",
+    "fmaheavy_warp_instr_per_add": 10643432704 / 262144,  # smsp__inst_executed_pipe_fmaheavy.sum: 40 601 (2 881 products x 432 IMAD.WIDE / 32 = 38 894, + moves)
+    "alu_warp_instr_per_add": 20703528846 / 262144,       # smsp__inst_executed_pipe_alu.sum: 78 978 (LOP3 & co)
+    "all_warp_instr_per_add": 32334274325 / 262144,       # smsp__inst_executed.sum: 123 345
+    "dram_bytes_per_add": (15.329295e9 + 16.664368e9) / 262144,  # dram__bytes_read.sum + dram__bytes_write.sum: 122.0 KB (algorithmic: 49.5 KB)
+    "pipe_pct_at_capture": {"alu": 61.24, "fmaheavy": 61.66, "adds_per_s_at_capture": 262144 / 58.120576e-3,
+                            "note": "sm__pipe_{alu,fmaheavy}_cycles_active.avg.pct_of_peak_sustained_elapsed of that capture (4.51 M adds/s); ncu's 100 % "
+                                    "is 2.0 (ALU) / 1.0 (IMAD.WIDE) warp-instructions per clock per SM; scaled by adds/s for this run"},
 }
 KARA8_PER_ADD = 1 + 30 * 3 + 6 * 465  # per bit: g (k=0), g, g_lo*p, g_hi*p (k=1..30); chain: sum_k k = 465 chunks x 6
 

@@ -2048,7 +2048,7 @@ static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm
             }
             dres = std::max(dres, c.items[t].degb);
         }
-        // L = 8 has at most 36 items per column; the bounds cannot differ (both follow result_bounds)
+        // L = 8 has at most 36 items per column, L = 16 at most 136; the bounds cannot differ (both follow result_bounds)
         if (c.items.size() > hmk::PREFIX_MAX_ITEMS || dres != o->degb[i]) return mul_generic_seq(ctx, a, b, o);
     }
     const size_t arena_words = cursor;

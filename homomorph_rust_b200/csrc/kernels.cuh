@@ -674,7 +674,7 @@ static __global__ void __launch_bounds__(256) xor_ops_kernel(const MulOp *__rest
 // prefix x_0 ^ ... ^ x_t.  One thread per (value, word); `width` is the widest destination.  Used by the multiplier
 // circuit (reference src/impls/numbers/common.rs:78-101): the carries of one column are x_t * (x_0 ^ ... ^ x_{t-1}),
 // so with the prefixes materialised all of a column's products are independent and go out in one launch.
-constexpr uint32_t PREFIX_MAX_ITEMS = 64;
+constexpr uint32_t PREFIX_MAX_ITEMS = 160; // L = 8: at most 36 items per column, L = 16: 136 (16 partial products + 120 carries)
 static __global__ void __launch_bounds__(256) prefix_xor_kernel(const MulOp *__restrict__ ops, uint32_t cnt, uint32_t width, uint64_t n) {
     // descriptors once per CTA into shared memory (cnt <= PREFIX_MAX_ITEMS, checked by the host)
     __shared__ View s_a[PREFIX_MAX_ITEMS], s_o[PREFIX_MAX_ITEMS];

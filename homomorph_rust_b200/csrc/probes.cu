@@ -17,6 +17,8 @@ namespace hmk {
 namespace {
 
 constexpr int ILP = 8;
+constexpr int UNROLL = 8; // probe instructions per loop iteration = ILP * UNROLL * per_iter: the loop counter's own ALU instructions
+                          // (add, compare) stay below 4 % of the stream
 constexpr int THREADS = 256;
 
 enum { P_IMADW = 0, P_LOP3 = 1, P_MIX12 = 2 };
@@ -29,15 +31,18 @@ template <int K> __global__ void __launch_bounds__(THREADS) pipe_probe_kernel(ui
         x[i] = (seed * 2654435761u + threadIdx.x * 40503u + i * 7919u) | 0x80000001u;
         y[i] = (seed * 40503u + (blockIdx.x * THREADS + threadIdx.x) * 2654435761u + i * 104729u) | 0x40000001u;
         z[i] = x[i] ^ (y[i] >> 3);
-        w[i] = x[i];
+        w[i] = (uint64_t)x[i] | ((uint64_t)y[i] << 32);
     }
     const long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < ILP; ++i) {
-            if (K == P_IMADW) // IMAD.WIDE.U32 Rd64, Ra, Rb, RZ — the low half of the product is the next multiplicand
-                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"((uint32_t)w[i]), "r"(y[i]));
+        for (int i0 = 0; i0 < ILP * UNROLL; ++i0) {
+            const int i = i0 % ILP;
+            if (K == P_IMADW) // IMAD.WIDE.U32 Rd64, Ra, Rb, RZ — both halves of the product are the next operands, so that neither
+                              // half is dead and the instruction cannot be narrowed to a 32-bit IMAD (operand values do not
+                              // change the timing: tools/ubench2.cu, 16-bit vs 32-bit operands)
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"((uint32_t)w[i]), "r"((uint32_t)(w[i] >> 32)));
             if (K == P_LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
             if (K == P_MIX12) { // one product, one 3-input XOR of its halves, one masked XOR feeding the next product
                 asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(x[i]), "r"(y[i]));
@@ -69,7 +74,7 @@ template <int K> cudaError_t run_probe(int sm_count, cudaStream_t stream, double
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (e == cudaSuccess) e = cudaEventCreate(&e0);
     if (e == cudaSuccess) e = cudaEventCreate(&e1);
-    int iters = 1 << 14;
+    int iters = 1 << 11;
     float ms = 0;
     float best_ms = 0;
     for (int pass = 0; pass < 4 && e == cudaSuccess; ++pass) { // calibration, then three full-length launches: the fastest counts
@@ -92,7 +97,7 @@ template <int K> cudaError_t run_probe(int sm_count, cudaStream_t stream, double
         double cyc = 0;
         for (int i = 0; i < blocks; ++i) cyc += (double)hclk[i];
         cyc /= blocks;
-        const double winstr = (double)blocks * (THREADS / 32) * (double)iters * ILP * per_iter;
+        const double winstr = (double)blocks * (THREADS / 32) * (double)iters * ILP * UNROLL * per_iter;
         out->warp_instr_per_s = winstr / (ms * 1e-3);
         out->cycle_counter_mhz = cyc / (ms * 1e3);
         out->ms = ms;

@@ -959,3 +959,41 @@ def test_multiword_kat_on_the_engine(oracle, hm):
             ctx.set_secret_key(hm.SecretKey.from_bytes(b[0].astype("<u8").tobytes()))
             got = ctx.poly_rem(ctx.upload(a, [a.shape[1]])).to_host()[0]
         assert np.array_equal(got[: want.size], want) and not got[want.size :].any(), c
+
+
+@pytest.mark.timeout(900, method="thread")
+def test_mul_u16_column_plan(oracle, hm):
+    """HomomorphicMultiplication at L = 16 (936 products, 680 carries per value) through the column-batched
+    plan — common.rs:66-105 — against the oracle at a small D (the oracle's bit-serial products make D = 256 minutes per
+    value), and at config A the batched plan against the one-product-per-launch plan."""
+    rng = np.random.default_rng(16)
+    params = (64, 16, 1, 16)  # d >= 64 delta (numbers.rs:47-50); D = 80 is not a multiple of 64: generic kernels
+    sk, pk, ctx = setup(oracle, hm, params, 45)
+    a = np.array([6, 65535, 300, 12345], dtype=np.uint16)
+    b = np.array([7, 65535, 200, 54321], dtype=np.uint16)
+    n, L = a.size, 16
+    ma, mb = masks_for(rng, n, L, params[3]), masks_for(rng, n, L, params[3])
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    l0 = ctx.kernel_launches()
+    r = ctx.apply2(hm.HomomorphicMultiplication, ca, cb)
+    launches = ctx.kernel_launches() - l0
+    assert launches < 120, launches  # one prefix pass + at most a few product launches per column, not one per product
+    oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
+    want, _ = oracle.apply(oracle.OP_MUL, oa, ob, L, threads=oracle.max_threads())
+    np.testing.assert_array_equal(r.to_host(), expected_padded(want, n, r.slot_words()))
+    od, _ = oracle.decrypt(sk, want, L)
+    np.testing.assert_array_equal(ctx.decrypt(r).view(np.uint8), od)
+    # config A: result degrees per column follow SURVEY.md A.3, and the two plans agree word for word
+    sk2, pk2, ctx2 = setup(oracle, hm, CONFIG_A, 46)
+    a2 = rng.integers(0, 65536, size=2, dtype=np.uint16)
+    b2 = rng.integers(0, 65536, size=2, dtype=np.uint16)
+    c2a, c2b = ctx2.encrypt(a2, seed=5), ctx2.encrypt(b2, seed=6)
+    p = ctx2.apply2(hm.HomomorphicMultiplication, c2a, c2b)
+    assert [int(x) // 256 for x in p.slot_degree_bounds()] == [2, 2, 4, 6, 10, 18, 32, 56, 98, 174, 314, 572, 1044, 1902, 3460, 6302]
+    lib = hm.lib()
+    try:
+        assert lib.hm_set_tuning(b"mul_circuit_sequential", 1) == 0
+        q = ctx2.apply2(hm.HomomorphicMultiplication, c2a, c2b)
+    finally:
+        lib.hm_set_tuning(b"mul_circuit_sequential", 0)
+    assert np.array_equal(p.to_host(), q.to_host())
