@@ -407,12 +407,15 @@ int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *
         default: {
             // enough (value, chunk) pairs to fill the GPU with one thread each?  -> Karatsuba thread kernel
             static const int no_thread = getenv("HM_MUL_NO_THREAD") ? atoi(getenv("HM_MUL_NO_THREAD")) : 0;
-            if (!no_thread && (uint64_t)n * xchunks_sum >= (g_mul_thread_min >= 0 ? (uint64_t)g_mul_thread_min : (uint64_t)ctx->sm_count * 128) &&
-                (uint64_t)n * cnt * xchunks_max <= ((uint64_t)1 << 22) && cnt <= 65535 && xchunks_max <= 65535) {
-                const size_t threads = (size_t)((n + 127) / 128) * 128 * cnt * xchunks_max;
-                PoolGuard scratch_guard(ctx);
-                CK(pool_alloc(ctx, &scratch_guard.p, threads * hmk::ADT_THREAD_WORDS * 4));
-                uint32_t *scratch = static_cast<uint32_t *>(scratch_guard.p);
+            const bool must_thread = smem_general == 0; // the warp kernel cannot stage these operands
+            auto xchunks_of = [&](size_t i) -> uint32_t {
+                return chunk32 ? (hmk::thread_mul_shape(h_ops[i]).nx + 31) / 32 : (2 * std::min(h_ops[i].a.w, h_ops[i].b.w) + 23) / 24;
+            };
+            const uint64_t rows = (uint64_t)((n + 127) / 128) * 128; // threads along x
+            const uint64_t max_threads = (uint64_t)1 << 22;          // 1 GiB of per-thread scratch at most per launch
+            const bool fits_one = (uint64_t)n * cnt * xchunks_max <= max_threads;
+            if ((must_thread || (fits_one && !no_thread && (uint64_t)n * xchunks_sum >= (g_mul_thread_min >= 0 ? (uint64_t)g_mul_thread_min : (uint64_t)ctx->sm_count * 128))) &&
+                rows * xchunks_max <= max_threads && cnt <= 65535 && xchunks_max <= 65535) {
                 // outputs are accumulated with atomics: zero them first (unless the caller already did)
                 for (size_t i = 0; i < cnt && !outputs_zeroed; ++i) {
                     const MulOp &o = h_ops[i];
@@ -423,11 +426,32 @@ int launch_mul_class(hm_context *ctx, int cls, const MulOp *d_ops, const MulOp *
                         if (zrc != HM_OK) return zrc;
                     }
                 }
-                const dim3 grid_t3((unsigned)((n + 127) / 128), (unsigned)cnt, (unsigned)xchunks_max);
-                if (chunk32) hmk::mul_thread32_kernel<<<grid_t3, 128, 0, ctx->stream>>>(d_ops, n, scratch);
-                else hmk::mul_thread_kernel<<<grid_t3, 128, 0, ctx->stream>>>(d_ops, n, scratch);
+                // one launch per run of products whose (rows x products x widest chunk count) stays within the scratch budget
+                for (size_t first = 0; first < cnt;) {
+                    size_t last = first;
+                    uint32_t xm = 0;
+                    while (last < cnt) {
+                        const uint32_t xn = std::max(xm, xchunks_of(last));
+                        if (last > first && rows * (last - first + 1) * xn > max_threads) break;
+                        xm = xn;
+                        ++last;
+                    }
+                    const size_t threads = (size_t)rows * (last - first) * xm;
+                    PoolGuard scratch_guard(ctx);
+                    CK(pool_alloc(ctx, &scratch_guard.p, threads * hmk::ADT_THREAD_WORDS * 4));
+                    uint32_t *scratch = static_cast<uint32_t *>(scratch_guard.p);
+                    const dim3 grid_t3((unsigned)(rows / 128), (unsigned)(last - first), (unsigned)xm);
+                    if (chunk32) hmk::mul_thread32_kernel<<<grid_t3, 128, 0, ctx->stream>>>(d_ops + first, n, scratch);
+                    else hmk::mul_thread_kernel<<<grid_t3, 128, 0, ctx->stream>>>(d_ops + first, n, scratch);
+                    if (last < cnt) {
+                        int prc = post_launch(ctx, "mul_thread kernel");
+                        if (prc != HM_OK) return prc;
+                    }
+                    first = last;
+                }
                 break;
             }
+            if (must_thread) return HM_ERR_UNSUPPORTED;
             const dim3 grid_w((unsigned)((n + 3) / 4), (unsigned)cnt);
             static const int old_generic = getenv("HM_MUL_OLD") ? atoi(getenv("HM_MUL_OLD")) : 0;
             if (old_generic) {
@@ -486,7 +510,9 @@ int launch_mul_ops(hm_context *ctx, const std::vector<MulOp> &ops_in, size_t n, 
             }
             per_warp = (per_warp + 3) & ~3u;
             smem = (size_t)per_warp * 4 * 4;
-            if (smem > ctx->smem_optin) return HM_ERR_UNSUPPORTED;
+            // operands too long for the warp kernel's shared-memory staging (u16 multiplier carries: tens of thousands of words):
+            // smem = 0 tells launch_mul_class to take the thread-per-chunk kernel whatever the batch size
+            if (smem > ctx->smem_optin) smem = 0;
         }
         rc = launch_mul_class(ctx, scls[first], ctx->d_ops + slot + first, sorted.data() + first, last - first, n, smem, per_warp,
                               outputs_zeroed, fuse_or);
