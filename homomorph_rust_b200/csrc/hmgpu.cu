@@ -35,6 +35,7 @@ static long g_mul_thread_min = -1; // minimum (values x chunks) for the thread-p
 static long g_mul_thread_chunk = 32; // 24 = the first thread-per-chunk kernel (3-way Karatsuba chunks)
 static long g_mul_circuit_seq = 0;
 static long g_adder_chain = getenv("HM_ADDER_CHAIN") ? atol(getenv("HM_ADDER_CHAIN")) : 4;   // 0 = round-1 thread kernels; else 10 * (window in smem) + CTAs per SM
+static long g_adder_wide_min = getenv("HM_ADDER_WIDE_MIN") ? atol(getenv("HM_ADDER_WIDE_MIN")) : 0; // D = 1024 chain kernel from this many values on (0 = 256 per SM, < 0 = never)
 static long g_adder_phases = getenv("HM_ADDER_PHASES") ? atol(getenv("HM_ADDER_PHASES")) : 0; // work units per value of the scheduled adder chain; 0 = by batch size
 static long g_host_chunk_mb = getenv("HM_HOST_CHUNK_MB") ? atol(getenv("HM_HOST_CHUNK_MB")) : 96; // per-stage bytes of the host-buffer pipeline
 static long g_pool_max_mb = getenv("HM_POOL_MAX_MB") ? atol(getenv("HM_POOL_MAX_MB")) : 16384; // larger batches use plain cudaMalloc
@@ -103,6 +104,9 @@ struct hm_context {
     size_t sched_words = 0;
 
     cudaMemPool_t pool = nullptr;  // private stream-ordered pool: nothing process-wide is reconfigured
+    cudaMemPool_t pool_big = nullptr; // second pool for batches above 1 GiB (results of circuits on big batches), so that small
+                                      // allocations cannot be carved out of a freed multi-GiB block and force the next big one
+                                      // to map fresh memory (seen: 350 ms instead of 62 ms per 11.45 GiB result)
     std::set<hm_batch *> live;     // batches still owned by callers; orphaned (device memory released) by hm_context_destroy
 };
 
@@ -232,7 +236,8 @@ int alloc_batch(hm_context *ctx, hm_batch *b) {
     // plain cudaMalloc: returning such a block to the pool costs ~0.5 s of unmapping at the next synchronisation.
     cudaError_t e;
     if (bytes <= ((size_t)(g_pool_max_mb > 0 ? g_pool_max_mb : 0) << 20)) {
-        e = pool_alloc(ctx, &b->d, bytes);
+        if (bytes > ((size_t)1 << 30) && ctx->pool_big) e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&b->d), bytes, ctx->pool_big, ctx->stream);
+        else e = pool_alloc(ctx, &b->d, bytes);
         b->pooled = true;
     } else {
         e = cudaMalloc(&b->d, bytes);
@@ -697,6 +702,12 @@ int hm_context_create(uint16_t d, uint16_t dp, uint16_t delta, uint16_t tau, int
         if (private_pool && cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess && ctx->pool) {
             uint64_t keep = UINT64_MAX;
             cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            if (cudaMemPoolCreate(&ctx->pool_big, &props) == cudaSuccess && ctx->pool_big) {
+                cudaMemPoolSetAttribute(ctx->pool_big, cudaMemPoolAttrReleaseThreshold, &keep);
+            } else {
+                ctx->pool_big = nullptr;
+                cudaGetLastError();
+            }
         } else {
             ctx->pool = nullptr; // the device's default pool
             cudaGetLastError();
@@ -747,6 +758,7 @@ void hm_context_destroy(hm_context *ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    if (ctx->pool_big) cudaMemPoolDestroy(ctx->pool_big);
     delete ctx;
 }
 
@@ -792,6 +804,10 @@ int hm_set_tuning(const char *key, long value) {
     if (strcmp(key, "adder_chain") == 0) {
         if (value != 0 && value != 3 && value != 4 && value != 12 && value != 13) return HM_ERR_INVALID_ARGUMENT;
         g_adder_chain = value;
+        return HM_OK;
+    }
+    if (strcmp(key, "adder_wide_min") == 0) {
+        g_adder_wide_min = value;
         return HM_OK;
     }
     if (strcmp(key, "adder_phases") == 0) {
@@ -2170,6 +2186,47 @@ static int adder_fast_path_wd(const hm_context *ctx, const hm_batch *a, const hm
     return words * 4 <= ctx->smem_optin ? wd : 0;
 }
 
+// the dynamically scheduled thread-per-value chain (kernels_adder.cu): scheduler state, phase plan, launch
+static int launch_chain_adder(hm_context *ctx, int wd, int variant, int ctas_per_sm, const hm_batch *a, const hm_batch *b, hm_batch *o) {
+    const size_t n = a->n;
+    const size_t words = hmk::adder_chain_sched_words(n);
+    if (ctx->sched_words < words) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_sched) cudaFree(ctx->d_sched);
+        ctx->d_sched = nullptr;
+        ctx->sched_words = 0;
+        CK(cudaMalloc(&ctx->d_sched, words * 4));
+        ctx->sched_words = words;
+    }
+    CK(cudaMemsetAsync(ctx->d_sched, 0, words * 4, ctx->stream));
+    hmk::AdderSched sc;
+    sc.counter = ctx->d_sched;
+    sc.done = ctx->d_sched + 1;
+    sc.ngroups = (uint32_t)((n + 31) / 32);
+    // Work units per value.  Splitting a value into phases pays when the batch is several waves of resident warps with a
+    // ragged last wave (2^18 values = 3.46 waves: 4.44 -> 4.51 M adds/s with 8 phases); on one or two exact waves the
+    // hand-over between warps only costs (75 776 values: 17.7 ms with 1 phase, 21.4 ms with 8).
+    const int phases = (int)g_adder_phases;
+    const uint64_t resident_warps = (uint64_t)ctx->sm_count * ctas_per_sm * 4;
+    // The D = 1024 chain (2 CTAs per SM) measured: one exact wave 265 k adds/s with 1 phase, 242 k with 8; 1.73 waves 230 k / 274 k.
+    const bool many_waves = wd == 32 ? (uint64_t)sc.ngroups * 10 >= resident_warps * 11 : (uint64_t)sc.ngroups * 2 >= resident_warps * 5;
+    const int auto_phases = many_waves ? 8 : 1;
+    hmk::adder_chain_plan(a->L, wd, (uint32_t)(phases > 0 ? phases : auto_phases), &sc);
+    CK(hmk::launch_adder_chain(wd, variant, a->d, b->d, o->d, n, a->L, make_layout(o), sc, ctx->sm_count, ctx->stream));
+    return post_launch(ctx, wd == 32 ? "adder_chain_wide_kernel" : "adder_chain_kernel");
+}
+
+// D = 1024 (config B): fresh operands on both sides and at least one value per resident thread of the thread-per-value chain
+// (2 CTAs of 128 threads per SM); smaller batches use the regrouped generic plan, which fills the GPU with (value, chunk)
+// threads (measured, u32 adds/s: 4 096 values 173 k generic / 49 k chain, 16 384: 220 k / 195 k, 37 888: 260 k / 265 k,
+// 65 536: 258 k / 274 k)
+static bool adder_wide_path(const hm_context *ctx, const hm_batch *a, const hm_batch *b) {
+    if (!ctx->has_pk || ctx->fresh_deg != 1024 || a->L < 2 || g_adder_wide_min < 0) return false;
+    for (uint32_t k = 0; k < a->L; ++k)
+        if (a->degb[k] != 1024 || b->degb[k] != 1024) return false;
+    return a->n >= (size_t)(g_adder_wide_min > 0 ? g_adder_wide_min : (long)ctx->sm_count * 256);
+}
+
 // runs `op` into the already allocated result batch o (layout = result_bounds of the operands)
 static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batch *b, hm_batch *o, bool force_generic) {
     const size_t n = a->n;
@@ -2213,6 +2270,10 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
         }
         case HM_OP_ADD: {
             size_t per_warp = 0;
+            if (!force_generic && adder_wide_path(ctx, a, b)) {
+                rc = launch_chain_adder(ctx, 32, 2, 2, a, b, o);
+                break;
+            }
             const int wd = force_generic ? 0 : adder_fast_path_wd(ctx, a, b, &per_warp);
             if (wd) {
                 int warps = (int)std::min<size_t>(4, ctx->smem_optin / per_warp);
@@ -2225,31 +2286,10 @@ static int apply2_exec(hm_context *ctx, int op, const hm_batch *a, const hm_batc
                 // smaller batches (and the chunks of the host pipeline) use the warp-per-value kernel
                 // HM_ADDER_CHAIN: 0 = the round-1 thread kernels below; otherwise the dynamically scheduled chain of kernels_adder.cu,
                 // value = 10 * (window in shared memory) + CTAs per SM.  HM_ADDER_PHASES = work units per value (default 4).
-                const int chain = (int)g_adder_chain, phases = (int)g_adder_phases;
+                const int chain = (int)g_adder_chain;
                 const bool big = n >= (g_adder_thread_min >= 0 ? (size_t)g_adder_thread_min : (size_t)ctx->sm_count * 96);
                 if (mode >= 3 && chain && big) {
-                    const size_t words = hmk::adder_chain_sched_words(n);
-                    if (ctx->sched_words < words) {
-                        CK(cudaStreamSynchronize(ctx->stream));
-                        if (ctx->d_sched) cudaFree(ctx->d_sched);
-                        ctx->d_sched = nullptr;
-                        ctx->sched_words = 0;
-                        CK(cudaMalloc(&ctx->d_sched, words * 4));
-                        ctx->sched_words = words;
-                    }
-                    CK(cudaMemsetAsync(ctx->d_sched, 0, words * 4, ctx->stream));
-                    hmk::AdderSched sc;
-                    sc.counter = ctx->d_sched;
-                    sc.done = ctx->d_sched + 1;
-                    sc.ngroups = (uint32_t)((n + 31) / 32);
-                    // Work units per value.  Splitting a value into phases pays when the batch is several waves of resident warps with a
-                    // ragged last wave (2^18 values = 3.46 waves: 4.44 -> 4.51 M adds/s with 8 phases); on one or two exact waves the
-                    // hand-over between warps only costs (75 776 values: 17.7 ms with 1 phase, 21.4 ms with 8).
-                    const uint64_t resident_warps = (uint64_t)ctx->sm_count * (chain % 10) * 4;
-                    const int auto_phases = (uint64_t)sc.ngroups * 2 >= resident_warps * 5 ? 8 : 1;
-                    hmk::adder_chain_plan(a->L, wd, (uint32_t)(phases > 0 ? phases : auto_phases), &sc);
-                    CK(hmk::launch_adder_chain(wd, chain, a->d, b->d, o->d, n, a->L, make_layout(o), sc, ctx->sm_count, ctx->stream));
-                    rc = post_launch(ctx, "adder_chain_kernel");
+                    rc = launch_chain_adder(ctx, wd, chain, chain % 10, a, b, o);
                     break;
                 }
                 if (mode >= 3 && wd == 8 && big) { // round-1 thread-per-value kernels; mode - 1 = CTAs per SM (cross-over measured: tools/adder_crossover.py)

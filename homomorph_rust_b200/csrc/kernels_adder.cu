@@ -267,9 +267,16 @@ __device__ __forceinline__ void chain_range(const uint64_t *__restrict__ Av, con
         };
         fill_first(cb0);
         if constexpr (TSM == 0) {
+            // the window starts as g_k + p_{k+1} (chunk 0 of c_{k+1} = m c_k + g_k, emitted as s_{k+1} = c_{k+1} + p_{k+1}), so that
+            // g and p_{k+1} are dead before the chunk loop begins: nothing but the window and one product lives across it
             uint32_t t[2 * CH];
 #pragma unroll
             for (int i = 0; i < 2 * CH; ++i) t[i] = 0;
+#pragma unroll
+            for (int i = 0; i < 2 * WD; ++i) t[i] = g[i];
+            t[2 * WD] = gtop;
+#pragma unroll
+            for (int i = 0; i <= WD; ++i) t[i] ^= pn[i];
             for (uint32_t j = 0; j <= k; ++j) {
                 uint2 *cur = (j & 1) ? cb1 : cb0, *nxt = (j & 1) ? cb0 : cb1;
                 if (j < k) {
@@ -285,13 +292,6 @@ __device__ __forceinline__ void chain_range(const uint64_t *__restrict__ Av, con
                     if (pref) asm volatile("cp.async.wait_group 1;" ::: "memory");
                     else asm volatile("cp.async.wait_group 0;" ::: "memory");
                     mul_chunk_acc<WD>(mb, cur, t);
-                }
-                if (j == 0) {
-#pragma unroll
-                    for (int i = 0; i < 2 * WD; ++i) t[i] ^= g[i];
-                    t[2 * WD] ^= gtop;
-#pragma unroll
-                    for (int i = 0; i <= WD; ++i) t[i] ^= pn[i];
                 }
 #pragma unroll
                 for (int q = 0; q < NPR; ++q)
@@ -371,6 +371,231 @@ __global__ void __launch_bounds__(CTA, MINB) adder_chain_kernel(const uint64_t *
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// D = 1024 (config B: d = d' = 512; WD = 32 words per fresh operand).  Same chain, same 24-word chunks of c_k and the same
+// 8x8-word products, but m_k has 96 words = FOUR sub-multipliers M_0..M_3 of 24 words:
+//     c_{k+1}[chunk o] = sum_q low(M_q * C_{o-q}) + high(M_q * C_{o-q-1})  (+ g_k)
+// so every output chunk takes four chunk products (24 8x8-word products) from the four most recent chunks of c_k, which sit
+// in a ring of five per-thread shared-memory chunk buffers (the fifth receives the cp.async prefetch).  Per thread: m_k 96
+// words + ring 120 words = 864 B of shared memory, 128 threads per CTA, 2 CTAs per SM (up to 255 registers); the
+// 8x8-word product runs at the same rate with 8 warps per SM as with 32 (profiles/r02_ubench2_pipes.txt).
+// The once-per-bit products (g = a b: 32 x 32 words, m = (1 + g) p: 64 x 32 words) go block by block through shared memory.
+// ----------------------------------------------------------------------------------------------------------------------
+constexpr int WIDE_M_PAIRS = 48;     // m_k: 96 words
+constexpr int WIDE_RING = 5;         // chunk buffers
+constexpr int WIDE_PAIRS = WIDE_M_PAIRS + WIDE_RING * 12;
+
+// out[(bi + bj) blocks ...] ^= x * y, operands and result in this thread's shared-memory columns (8-word blocks = 4 pairs)
+__device__ __forceinline__ void smem_mul_acc8(const uint2 *x, int nbx, const uint2 *y, int nby, uint2 *out) {
+#pragma unroll 1
+    for (int bi = 0; bi < nbx; ++bi) {
+#pragma unroll 1
+        for (int bj = 0; bj < nby; ++bj) {
+            uint32_t a[8], b[8], r[16];
+            load_block<8>(a, x + bi * 4 * CTA);
+            load_block<8>(b, y + bj * 4 * CTA);
+            clmul_kara<8>(a, b, r);
+            uint2 *o = out + (bi + bj) * 4 * CTA;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                uint2 w = o[q * CTA];
+                w.x ^= r[2 * q];
+                w.y ^= r[2 * q + 1];
+                o[q * CTA] = w;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void chain_range_wide(const uint64_t *__restrict__ Av, const uint64_t *__restrict__ Bv, uint32_t *__restrict__ Ov,
+                                                 const Layout &lo, uint32_t L, uint32_t k0, uint32_t k1, uint2 *mb, uint2 *ring) {
+    constexpr int WD = 32, WF = WD / 2 + 1, CH = 24, NPR = 12;
+    uint32_t *mbw = reinterpret_cast<uint32_t *>(mb);     // word i of a column: w[(i / 2) * CTA * 2 + (i & 1)]
+    uint32_t *ringw = reinterpret_cast<uint32_t *>(ring);
+    auto W = [](uint32_t *col, int i) -> uint32_t & { return col[(i >> 1) * CTA * 2 + (i & 1)]; };
+    for (uint32_t k = k0; k < k1; ++k) {
+        const uint64_t *ak = Av + (size_t)k * WF, *bk = Bv + (size_t)k * WF;
+        const uint32_t atop = (uint32_t)__ldg(ak + WD / 2) & 1u, btop = (uint32_t)__ldg(bk + WD / 2) & 1u;
+        const uint32_t ptop = atop ^ btop, gtop = atop & btop;
+        if (k == 0) { // s_0 = p_0
+            uint32_t *dst = Ov + 2 * lo.off[0];
+            const uint32_t wo = 2 * (lo.off[1] - lo.off[0]);
+            for (int j = 0; j < WD / 2; ++j) {
+                const uint64_t x = __ldg(ak + j) ^ __ldg(bk + j);
+                dst[2 * j] = (uint32_t)x;
+                dst[2 * j + 1] = (uint32_t)(x >> 32);
+            }
+            dst[WD] = ptop;
+            for (uint32_t j = WD + 1; j < wo; ++j) dst[j] = 0;
+        }
+        if (k + 1 == L) break; // no carry out of the last bit (common.rs:47-49)
+        // ---- g = a b into mb[0 .. 64) (+ gtop), operands staged in the ring: a' at pairs [0, 16), b' at [16, 32) ----
+        for (int j = 0; j < WD / 2; ++j) {
+            const uint64_t x = __ldg(ak + j), y = __ldg(bk + j);
+            ring[j * CTA] = make_uint2((uint32_t)x, (uint32_t)(x >> 32));
+            ring[(16 + j) * CTA] = make_uint2((uint32_t)y, (uint32_t)(y >> 32));
+        }
+        for (int q = 0; q < WIDE_M_PAIRS; ++q) mb[q * CTA] = make_uint2(0u, 0u);
+        smem_mul_acc8(ring, 4, ring + 16 * CTA, 4, mb);
+        {
+            const uint32_t ma = 0u - atop, mbm = 0u - btop; // X^1024 (at b' + bt a') into words [32, 64)
+            for (int j = 0; j < WD / 2; ++j) {
+                const uint2 xa = ring[j * CTA], xb = ring[(16 + j) * CTA];
+                uint2 w = mb[(16 + j) * CTA];
+                w.x ^= (xb.x & ma) ^ (xa.x & mbm);
+                w.y ^= (xb.y & ma) ^ (xa.y & mbm);
+                mb[(16 + j) * CTA] = w;
+            }
+        }
+        // ---- slot k + 1 starts as g_k + p_{k+1}: the chain adds m_k c_k chunk by chunk on top of it (read back below) ----
+        uint32_t *sdst = Ov + 2 * lo.off[k + 1];
+        const uint32_t swo = 2 * (lo.off[k + 2] - lo.off[k + 1]);
+        {
+            const uint64_t *an = Av + (size_t)(k + 1) * WF, *bn = Bv + (size_t)(k + 1) * WF;
+            for (int j = 0; j < 32; ++j) { // 64 words of g; the first 32 (+1) also take p_{k+1}
+                uint2 w = mb[j * CTA];
+                if (j < WD / 2) {
+                    const uint64_t pn = __ldg(an + j) ^ __ldg(bn + j);
+                    w.x ^= (uint32_t)pn;
+                    w.y ^= (uint32_t)(pn >> 32);
+                }
+                if (j == WD / 2) w.x ^= (uint32_t)(__ldg(an + WD / 2) ^ __ldg(bn + WD / 2)) & 1u;
+                *reinterpret_cast<uint2 *>(sdst + 2 * j) = w;
+            }
+            sdst[64] = gtop;
+            const uint32_t init_end = (k == 0) ? swo : 72u; // k >= 1: the chain reads back chunks 0..2 (72 words) only
+            for (uint32_t j = 65; j < init_end && j < swo; ++j) sdst[j] = 0;
+        }
+        if (k == 0) continue; // c_1 = g_0
+        // ---- m = p + g p (96 words) into mb; g' moves to ring pairs [0, 32), p' to ring pairs [32, 48) ----
+        for (int j = 0; j < 32; ++j) ring[j * CTA] = mb[j * CTA];
+        for (int j = 0; j < WD / 2; ++j) {
+            const uint64_t x = __ldg(ak + j) ^ __ldg(bk + j);
+            ring[(32 + j) * CTA] = make_uint2((uint32_t)x, (uint32_t)(x >> 32));
+        }
+        {
+            const uint32_t mp = 0u - ptop, mg = 0u - gtop;
+            for (int j = 0; j < WIDE_M_PAIRS; ++j) { // p' + X^1024 (pt g' + pt) + X^2048 gt p'
+                uint2 w = make_uint2(0u, 0u);
+                if (j < 16) w = ring[(32 + j) * CTA];
+                if (j >= 16) {
+                    const uint2 gq = ring[(j - 16) * CTA];
+                    w.x ^= gq.x & mp;
+                    w.y ^= gq.y & mp;
+                }
+                if (j >= 32) {
+                    const uint2 pq = ring[(32 + j - 32) * CTA];
+                    w.x ^= pq.x & mg;
+                    w.y ^= pq.y & mg;
+                }
+                if (j == 16) w.x ^= ptop;
+                mb[j * CTA] = w;
+            }
+        }
+        smem_mul_acc8(ring, 8, ring + 32 * CTA, 4, mb); // + g' p'
+        // ---- chain ----
+        const uint32_t *cslot = Ov + 2 * lo.off[k]; // s_k = c_k + p_k
+        const uint32_t len = 96 * k - 31;           // words of c_k
+        const uint32_t nch = 4 * k - 1;             // chunks of c_k; the last one holds 17 valid words
+        auto ring_slot = [&](uint32_t j) -> uint2 * { return ring + (j % WIDE_RING) * NPR * CTA; };
+        auto fill_sync = [&](uint32_t j) { // chunks 0 and 1 carry p_k (words 0..32), the last chunk is ragged
+            uint2 *dstb = ring_slot(j);
+            for (int q = 0; q < NPR; ++q) {
+                uint32_t v2[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t w = CH * j + 2 * q + h;
+                    uint32_t val = (w < len) ? cslot[w] : 0u;
+                    if (w < (uint32_t)WD) {
+                        const uint64_t x = __ldg(ak + (w >> 1)) ^ __ldg(bk + (w >> 1));
+                        val ^= (w & 1) ? (uint32_t)(x >> 32) : (uint32_t)x;
+                    } else if (w == (uint32_t)WD) {
+                        val ^= ptop;
+                    }
+                    v2[h] = val;
+                }
+                dstb[q * CTA] = make_uint2(v2[0], v2[1]);
+            }
+        };
+        auto fill_async = [&](uint32_t j) {
+            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ring_slot(j));
+            const uint32_t *src = cslot + CH * j;
+#pragma unroll
+            for (int q = 0; q < NPR; ++q)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + q * CTA * 8), "l"(src + 2 * q) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        fill_sync(0);
+        if (nch > 1) fill_sync(1);
+        uint32_t t[2 * CH];
+#pragma unroll
+        for (int i = 0; i < 2 * CH; ++i) t[i] = 0;
+        const uint32_t nout = nch + 4; // output chunks 0 .. nch + 3
+        for (uint32_t o = 0; o < nout; ++o) {
+            bool pref = false;
+            if (o >= 1 && o + 1 < nch) { // chunk o + 1 replaces chunk o - 4 in the ring (chunks 0 and 1 are already there)
+                if (o + 2 < nch) {
+                    fill_async(o + 1);
+                    pref = true;
+                } else {
+                    fill_sync(o + 1);
+                }
+            }
+            if (pref) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll 1
+            for (uint32_t q = 0; q < 4; ++q) {
+                if (o >= q && o - q < nch) mul_chunk_acc<8>(mb + q * NPR * CTA, ring_slot(o - q), t);
+            }
+            if (o < 3) { // + g_k + p_{k+1}, parked in the slot itself
+#pragma unroll
+                for (int q = 0; q < NPR; ++q) {
+                    const uint2 w = *reinterpret_cast<const uint2 *>(sdst + CH * o + 2 * q);
+                    t[2 * q] ^= w.x;
+                    t[2 * q + 1] ^= w.y;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NPR; ++q)
+                if (CH * o + 2 * q < swo) *reinterpret_cast<uint2 *>(sdst + CH * o + 2 * q) = make_uint2(t[2 * q], t[2 * q + 1]);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                t[i] = t[CH + i];
+                t[CH + i] = 0;
+            }
+        }
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(CTA, MINB) adder_chain_wide_kernel(const uint64_t *__restrict__ A, const uint64_t *__restrict__ B,
+                                                                    uint64_t *__restrict__ O, uint64_t n, uint32_t L, Layout lo, AdderSched sc) {
+    constexpr int WF = 17;
+    extern __shared__ __align__(16) uint2 chain_smem[];
+    uint2 *mb = chain_smem + threadIdx.x, *ring = mb + WIDE_M_PAIRS * CTA;
+    const int lane = threadIdx.x & 31;
+    const uint32_t total = sc.ngroups * sc.nphases;
+    for (;;) {
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(sc.counter, 1u);
+        unit = __shfl_sync(FULL, unit, 0);
+        if (unit >= total) break;
+        const uint32_t ph = unit / sc.ngroups, grp = unit - ph * sc.ngroups;
+        if (ph) {
+            while (ld_acquire_u32(sc.done + grp) < ph) __nanosleep(256);
+        }
+        const uint64_t v = (uint64_t)grp * 32 + lane;
+        if (v < n)
+            chain_range_wide(A + v * (uint64_t)L * WF, B + v * (uint64_t)L * WF, reinterpret_cast<uint32_t *>(O + v * (uint64_t)lo.value_words), lo, L,
+                             sc.kb[ph], sc.kb[ph + 1], mb, ring);
+        if (ph + 1 < sc.nphases) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_u32(sc.done + grp, ph + 1);
+        }
+    }
+}
+
 } // namespace
 
 size_t adder_chain_sched_words(uint64_t n) { return 1 + (size_t)((n + 31) / 32); }
@@ -421,6 +646,16 @@ cudaError_t launch_adder_chain(int wd, int variant, const uint64_t *A, const uin
     } else if (wd == 4) {
         if (tsm == 0) return launch_one<4, 0, 4>(A, B, O, n, L, lo, sc, sm_count, stream);
         return launch_one<4, 1, 4>(A, B, O, n, L, lo, sc, sm_count, stream);
+    } else if (wd == 32) { // D = 1024: four sub-multipliers, 2 CTAs of 128 threads per SM
+        auto kern = adder_chain_wide_kernel<2>;
+        const size_t smem = (size_t)WIDE_PAIRS * CTA * 8;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        uint64_t blocks = (uint64_t)sm_count * 2;
+        if (blocks * (CTA / 32) > sc.ngroups) blocks = ((uint64_t)sc.ngroups + CTA / 32 - 1) / (CTA / 32);
+        if (blocks < 1) blocks = 1;
+        kern<<<(unsigned)blocks, CTA, smem, stream>>>(A, B, O, n, L, lo, sc);
+        return cudaGetLastError();
     }
     return cudaErrorInvalidValue;
 }

@@ -722,6 +722,44 @@ def test_add_chain_kernel_variants(oracle, hm, params, dtype, n, chain, phases):
     np.testing.assert_array_equal(ctx.decrypt(r_chain)[:k].view(np.uint8), od)
 
 
+@pytest.mark.parametrize("dtype,n,phases", [(np.uint8, 70, 1), (np.uint32, 37, 8), (np.uint16, 33, 3), (np.uint64, 3, 2)])
+def test_add_chain_kernel_wide(oracle, hm, dtype, n, phases):
+    """Config B (d = d' = 512, D = 1024): the thread-per-value chain with four sub-multipliers (adder_chain_wide_kernel) forced
+    on small ragged batches: one launch, bit-exact against the regrouped generic plan and against the oracle
+    (common.rs:37-56)."""
+    rng = np.random.default_rng(n * 17 + phases)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_B, 31)
+    tau = CONFIG_B[3]
+    L = np.dtype(dtype).itemsize * 8
+    a = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    b = rng.integers(0, np.iinfo(dtype).max, size=n, dtype=dtype, endpoint=True)
+    ma, mb = masks_for(rng, n, L, tau), masks_for(rng, n, L, tau)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    lib = hm.lib()
+    try:
+        assert lib.hm_set_tuning(b"adder_wide_min", 1) == 0
+        assert lib.hm_set_tuning(b"adder_phases", phases) == 0
+        l0 = ctx.kernel_launches()
+        r_wide = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+        assert ctx.kernel_launches() - l0 == 1  # one fused launch
+        got = r_wide.to_host()
+        assert lib.hm_set_tuning(b"adder_wide_min", -1) == 0
+        l0 = ctx.kernel_launches()
+        r_gen = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+        assert ctx.kernel_launches() - l0 > 1
+    finally:
+        lib.hm_set_tuning(b"adder_wide_min", 0)
+        lib.hm_set_tuning(b"adder_phases", 0)
+    np.testing.assert_array_equal(got, r_gen.to_host())
+    k = min(n, 6 if L > 16 else 24)
+    mbytes = (tau + 7) // 8
+    want, _ = oracle.apply(oracle.OP_ADD, oracle_encrypt(oracle, pk, a[:k], ma[: k * L * mbytes]), oracle_encrypt(oracle, pk, b[:k], mb[: k * L * mbytes]), L,
+                           threads=oracle.max_threads())
+    np.testing.assert_array_equal(got[:k], expected_padded(want, k, r_wide.slot_words()))
+    od, _ = oracle.decrypt(sk, want, L)
+    np.testing.assert_array_equal(ctx.decrypt(r_wide)[:k].view(np.uint8), od)
+
+
 def test_into_and_device_entry_points(oracle, hm):
     """The entry points bench.py times — hm_encrypt_device_into, hm_apply2_into, hm_poly_mulrem_into, hm_decrypt_device —
     compared word for word with the oracle (they share the kernels of the allocating calls, but are separate ABI paths)."""
