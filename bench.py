@@ -490,11 +490,22 @@ def run_ours(args, rank, local_rank, world):
         s = timed(encd, reps=20)
         props = torch.cuda.get_device_properties(local_rank)
         sm_count, sm_clk = props.multi_processor_count, getattr(props, "clock_rate", 1965000) * 1e3
-        extra["encrypt"] = {"value": n / s, "unit": "u32/s", "kernel": "encrypt_tab6b_kernel", "ms": s * 1e3,
+        extra["encrypt"] = {"value": n / s, "unit": "u32/s", "kernel": "encrypt_tab4_kernel<false> (masks read from HBM)", "ms": s * 1e3,
                             "hbm_GBps": n * 1792 / s / 1e9, "hbm_frac": n * 1792 / s / 1e9 / hbm_peak,
-                            "smem_frac": (n * L / s) * (32.0 / 6.0) / (sm_count * sm_clk),
-                            "note": "table lookups: 640 B of shared-memory reads per 56 B of HBM traffic, so the binding roofline is the "
-                                    "shared-memory pipe (smem_frac = LDS wavefront cycles needed / available), not HBM"}
+                            "smem_frac": (n * L / s) * 4.0 / (sm_count * sm_clk),
+                            "note": "table lookups: 16 x 32 B of shared-memory reads per 56 B of HBM traffic (4 LDS wavefronts per "
+                                    "bit-ciphertext), so the shared-memory pipe and instruction issue bind before HBM does "
+                                    "(smem_frac = LDS wavefront cycles needed / available)"}
+
+        def encs():
+            rc = lib.hm_encrypt_device_seeded_into(ctx._h, dv.data_ptr(), n, L, 12345, 0, ce._h)
+            assert rc == 0, rc
+
+        s = timed(encs, reps=20)
+        extra["encrypt_seeded"] = {"value": n / s, "unit": "u32/s", "kernel": "encrypt_tab4_kernel<true> (Philox masks drawn in the kernel)",
+                                   "ms": s * 1e3, "hbm_GBps": n * 1284 / s / 1e9, "hbm_frac": n * 1284 / s / 1e9 / hbm_peak,
+                                   "smem_frac": (n * L / s) * 4.0 / (sm_count * sm_clk),
+                                   "note": "no mask buffer: 40 B written per bit-ciphertext, 4 B of plaintext read per u32"}
         ce.free()
         del dm, dv
         # end-to-end encryption, host plaintexts in -> ciphertexts resident in HBM: (i) host-generated masks cross PCIe

@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
         "hm_encrypt": (C.c_int, [vp, vp, sz, C.c_uint32, vp, C.POINTER(vp)]),
         "hm_encrypt_device": (C.c_int, [vp, vp, sz, C.c_uint32, vp, C.POINTER(vp)]),
         "hm_encrypt_device_into": (C.c_int, [vp, vp, sz, C.c_uint32, vp, vp]),
+        "hm_encrypt_device_seeded_into": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint64, C.c_uint64, vp]),
         "hm_masks_generate_host": (C.c_int, [u16, sz, C.c_uint64, vp]),
         "hm_masks_generate_device": (C.c_int, [vp, sz, C.c_uint64, vp]),
         "hm_encrypt_seeded": (C.c_int, [vp, vp, sz, C.c_uint32, C.c_uint64, C.POINTER(vp)]),

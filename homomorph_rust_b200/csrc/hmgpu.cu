@@ -92,6 +92,8 @@ struct hm_context {
     bool enc_table_in_smem = false;
     uint64_t *d_enc_table = nullptr;
     uint64_t *d_enc_table6 = nullptr; // bank-partitioned copy for encrypt_tab6_kernel (config A shape only)
+    uint64_t *d_enc_table4 = nullptr; // four-class 32-byte-row copy for encrypt_tab4_kernel (config A shape only)
+    uint32_t enc_topmask[4] = {0, 0, 0, 0}; // bit i = coefficient of X^256 of T_i (the fifth word of a row, computed instead of looked up)
 
     // ring of op descriptors: pinned host staging + device copy, so that launches need no host synchronisation
     MulOp *d_ops = nullptr;
@@ -335,6 +337,9 @@ void clear_secret(hm_context *ctx) {
 void clear_public(hm_context *ctx) {
     if (ctx->d_enc_table) cudaFree(ctx->d_enc_table);
     if (ctx->d_enc_table6) cudaFree(ctx->d_enc_table6);
+    if (ctx->d_enc_table4) cudaFree(ctx->d_enc_table4);
+    ctx->d_enc_table4 = nullptr;
+    for (uint32_t &m : ctx->enc_topmask) m = 0;
     ctx->d_enc_table = nullptr;
     ctx->d_enc_table6 = nullptr;
     ctx->T_host.clear();
@@ -944,6 +949,21 @@ int hm_set_public_key(hm_context *ctx, const uint8_t *const *polys, const size_t
         CK(cudaMemcpyAsync(ctx->d_enc_table6, t6.data(), t6.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    if (in_smem && wb == 8 && wf == 5 && maxdeg == 256 && tau == 128 && (size_t)hmk::ENC4_TABLE_BYTES + 65536 + 1024 <= ctx->smem_optin) {
+        // encrypt_tab4_kernel: words 0..3 of row (g, e) at byte (t >> 1) * 65536 + e * 256 + (t & 1) * 128 + k * 32, g = 4 t + k
+        std::vector<uint64_t> t4((size_t)hmk::ENC4_TABLE_BYTES / 8, 0);
+        for (uint32_t g = 0; g < groups; ++g)
+            for (uint32_t e = 0; e < 256; ++e) {
+                const uint32_t t = g / 4, k = g % 4;
+                const size_t byte = (size_t)(t >> 1) * 65536 + (size_t)e * 256 + (t & 1) * 128 + k * 32;
+                for (uint32_t j = 0; j < 4; ++j) t4[byte / 8 + j] = tab[((size_t)(g << 8) + e) * 5 + j];
+            }
+        for (uint32_t i = 0; i < 128; ++i)
+            if (T[i].size() > 4 && (T[i][4] & 1)) ctx->enc_topmask[i / 32] |= 1u << (i % 32);
+        CK(cudaMalloc(&ctx->d_enc_table4, t4.size() * 8));
+        CK(cudaMemcpyAsync(ctx->d_enc_table4, t4.data(), t4.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->enc_wb = wb;
     ctx->enc_groups = groups;
     ctx->enc_table_words = (uint32_t)tab.size();
@@ -1354,7 +1374,14 @@ void hm_host_free(void *p) {
 }
 
 // ---- encrypt / decrypt ------------------------------------------------------------------------
-static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks, hm_batch *b);
+// d_masks == nullptr: masks drawn inside the kernel from Philox(seed) at stream position first_unit (only where
+// encrypt_fuses_masks(ctx, n * L) says so)
+static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks, hm_batch *b, uint64_t seed = 0,
+                        uint64_t first_unit = 0);
+static const int g_enc_mode = getenv("HM_ENC_MODE") ? atoi(getenv("HM_ENC_MODE")) : 2; // 2 = encrypt_tab4_kernel, 1 = encrypt_tab6(b)_kernel, 0 = encrypt_tab_kernel
+static bool encrypt_fuses_masks(const hm_context *ctx, uint64_t units) {
+    return g_enc_mode == 2 && ctx->d_enc_table4 && units < ((uint64_t)1 << 31);
+}
 
 int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
                       hm_batch **out) {
@@ -1388,8 +1415,32 @@ int hm_encrypt_device_into(hm_context *ctx, const uint8_t *d_values, size_t n, u
     return encrypt_exec(ctx, d_values, n, L, d_masks, out);
 }
 
-static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks, hm_batch *b) {
+static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks, hm_batch *b, uint64_t seed,
+                        uint64_t first_unit) {
     if (n == 0) return HM_OK;
+    if (encrypt_fuses_masks(ctx, (uint64_t)n * L) && (!d_masks || ((uintptr_t)d_masks % 16) == 0)) {
+        hmk::Enc4Params q;
+        q.values = d_values;
+        q.masks = d_masks;
+        q.out = b->d;
+        q.units = (uint32_t)((uint64_t)n * L);
+        for (int i = 0; i < 4; ++i) q.topmask[i] = ctx->enc_topmask[i];
+        q.seed = seed;
+        q.first_unit = first_unit;
+        const size_t smem = (size_t)hmk::ENC4_TABLE_BYTES + 65536; // the table starts on a 64 KB boundary of the shared window
+        const int grid = grid_for(ctx, ((uint64_t)q.units + 31) / 32 * 32, hmk::ENC4_THREADS, 1);
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(ctx->d_enc_table4);
+        if (d_masks) {
+            CK(cudaFuncSetAttribute(hmk::encrypt_tab4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hmk::encrypt_tab4_kernel<false><<<grid, hmk::ENC4_THREADS, smem, ctx->stream>>>(q, t4);
+        } else {
+            CK(cudaFuncSetAttribute(hmk::encrypt_tab4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hmk::encrypt_tab4_kernel<true><<<grid, hmk::ENC4_THREADS, smem, ctx->stream>>>(q, t4);
+        }
+        LAUNCHED("encrypt_tab4_kernel");
+        return HM_OK;
+    }
+    if (!d_masks) return HM_ERR_INVALID_ARGUMENT;
     hmk::EncParams p;
     p.values = d_values;
     p.masks = d_masks;
@@ -1409,8 +1460,8 @@ static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint
     if (ctx->enc_table_in_smem && masks_aligned && p.wf == 17 && ctx->tau == 256 && p.wb == 4 &&
         table_bytes + 2 * (size_t)256 * 17 * 8 <= ctx->smem_optin) // 256-thread CTAs: table 136 KB + 2 x 34 KB of staging
         path = 2;
-    static const int enc_mode = getenv("HM_ENC_MODE") ? atoi(getenv("HM_ENC_MODE")) : 1;
-    if (path == 1 && enc_mode == 1 && ctx->d_enc_table6) {
+    const int enc_mode = g_enc_mode;
+    if (path == 1 && enc_mode >= 1 && ctx->d_enc_table6) {
         const size_t smem = (size_t)hmk::ENC6_SLOTS * 256 * 128;
         CK(cudaFuncSetAttribute(hmk::encrypt_tab6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int grid = grid_for(ctx, (p.units + 5) / 6 * 32, hmk::ENC6_THREADS, 1);
@@ -1460,14 +1511,29 @@ static int encrypt_host_impl(hm_context *ctx, const uint8_t *values, size_t n, u
     const size_t vbytes = n * (L / 8), mbytes = n * L * ((ctx->tau + 7u) / 8u);
     PoolGuard dv(ctx), dm(ctx);
     CK(pool_alloc(ctx, &dv.p, std::max<size_t>(vbytes, 16)));
-    CK(pool_alloc(ctx, &dm.p, std::max<size_t>(mbytes, 16)));
+    const bool fused_masks = !masks && encrypt_fuses_masks(ctx, (uint64_t)n * L); // Philox inside the encrypt kernel: no mask buffer
+    if (!fused_masks) CK(pool_alloc(ctx, &dm.p, std::max<size_t>(mbytes, 16)));
     if (n) {
         CK(cudaMemcpyAsync(dv.p, values, vbytes, cudaMemcpyHostToDevice, ctx->stream));
         if (masks) CK(cudaMemcpyAsync(dm.p, masks, mbytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     int rc = HM_OK;
-    if (!masks) rc = masks_generate_device_at(ctx, n * L, seed, first_unit, static_cast<uint8_t *>(dm.p));
-    if (rc == HM_OK) rc = hm_encrypt_device(ctx, static_cast<const uint8_t *>(dv.p), n, L, static_cast<const uint8_t *>(dm.p), out);
+    if (!masks && !fused_masks) rc = masks_generate_device_at(ctx, n * L, seed, first_unit, static_cast<uint8_t *>(dm.p));
+    if (rc == HM_OK && fused_masks) {
+        std::vector<uint64_t> degb(L, ctx->fresh_deg);
+        int nb_status = HM_OK;
+        hm_batch *b = new_batch(ctx, n, L, degb.data(), &nb_status);
+        if (!b) return nb_status;
+        rc = alloc_batch(ctx, b);
+        if (rc == HM_OK) rc = encrypt_exec(ctx, static_cast<const uint8_t *>(dv.p), n, L, nullptr, b, seed, first_unit);
+        if (rc != HM_OK) {
+            hm_batch_free(ctx, b);
+            return rc;
+        }
+        *out = b;
+    } else if (rc == HM_OK) {
+        rc = hm_encrypt_device(ctx, static_cast<const uint8_t *>(dv.p), n, L, static_cast<const uint8_t *>(dm.p), out);
+    }
     if (sync) {
         cudaError_t e = cudaStreamSynchronize(ctx->stream); // the caller's host buffers may be reused after return
         if (rc == HM_OK && e != cudaSuccess) {
@@ -1522,6 +1588,23 @@ int hm_encrypt_seeded(hm_context *ctx, const uint8_t *values, size_t n, uint32_t
 int hm_encrypt_seeded_at(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, uint64_t seed, uint64_t first_unit, int sync,
                          hm_batch **out) {
     return encrypt_host_impl(ctx, values, n, L, nullptr, seed, first_unit, sync != 0, out);
+}
+
+int hm_encrypt_device_seeded_into(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, uint64_t seed, uint64_t first_unit,
+                                  hm_batch *out) {
+    if (!ctx || !out || (!d_values && n)) return HM_ERR_INVALID_ARGUMENT;
+    if (!ctx->has_pk) return HM_ERR_PUBLIC_KEY_UNSET;
+    if (out->n != n || out->L != L || L % 8 != 0) return HM_ERR_INVALID_ARGUMENT;
+    for (uint32_t k = 0; k < L; ++k)
+        if (out->w[k] != ctx->wf) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    out->degb.assign(L, ctx->fresh_deg);
+    if (encrypt_fuses_masks(ctx, (uint64_t)n * L)) return encrypt_exec(ctx, d_values, n, L, nullptr, out, seed, first_unit);
+    PoolGuard dm(ctx);
+    CK(pool_alloc(ctx, &dm.p, std::max<size_t>(n * L * ((ctx->tau + 7u) / 8u), 16)));
+    int rc = masks_generate_device_at(ctx, n * L, seed, first_unit, static_cast<uint8_t *>(dm.p));
+    if (rc == HM_OK) rc = encrypt_exec(ctx, d_values, n, L, static_cast<const uint8_t *>(dm.p), out);
+    return rc;
 }
 
 int hm_decrypt_device(hm_context *ctx, const hm_batch *b, uint8_t *d_values_out) {

@@ -413,6 +413,123 @@ static __global__ void __launch_bounds__(ENC6_THREADS, 1) encrypt_tab6b_kernel(E
     }
 }
 
+// Round-2 successor (config A shape: tau = 128, D = 256): TWO lanes per bit-ciphertext (16 bytes of the row each, LDS.128),
+// 16 bit-ciphertexts per warp pass, and rows of 32 bytes.  Word 4 of a fresh ciphertext holds only the coefficient of X^256,
+// which is parity(mask AND topmask) with topmask_i = [X^256] T_i — so the table keeps words 0..3 only: 16 groups x 256 rows x
+// 32 B = 128 KB with no padding, in FOUR bank classes:
+//   line(t, e) = 128 bytes: [ row(group 4t, e) | row(4t+1, e) | row(4t+2, e) | row(4t+3, e) ],   t = 0..3 = mask word
+// A quarter-warp (8 lanes = 4 ciphertexts x 2 halves, the unit an LDS.128 is served in) reads four different classes in every
+// step (class = (position + step) % 4), i.e. all 32 banks once: conflict-free for random row indices.  4 shared-memory
+// wavefronts per bit-ciphertext instead of 5.6, and 16 ciphertexts per 16 LDS instead of 6.
+// The address of a lookup is ONE instruction: lines are 256 bytes apart (the lines of mask words t and t+1 interleave) and the
+// table starts on a 64 KB boundary of the shared window, so PRMT drops the mask byte into bits 8..15 of a per-lane base
+// address (class and half offsets in bits 0..7, table base above); t picks the LDS immediate.
+// SEEDED: the masks come from Philox4x32-10 inside the kernel (same stream as mask_fill_kernel / hm_masks_generate_host):
+// every lane draws the mask of one of the 32 ciphertexts of a double pass, the pass fetches its four words by shuffle — no
+// mask buffer in HBM (16 B written + 16 B read per bit-ciphertext before).
+constexpr int ENC4_THREADS = 1024;
+constexpr int ENC4_TABLE_BYTES = 4 * 256 * 128;
+struct Enc4Params {
+    const uint8_t *values;
+    const uint8_t *masks; // unused when SEEDED
+    uint64_t *out;
+    uint32_t units;
+    uint32_t topmask[4];
+    uint64_t seed, first_unit;
+};
+template <int IMM> __device__ __forceinline__ uint4 lds128_off(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4 + %5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(IMM));
+    return v;
+}
+template <int T> __device__ __forceinline__ void enc4_word(uint32_t m, const uint32_t (&bb)[4], const uint32_t (&sel)[4], uint32_t (&acc)[4]) {
+    uint4 x[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        uint32_t addr;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(addr) : "r"(m), "r"(bb[s]), "r"(sel[s]));
+        x[s] = lds128_off<(T >> 1) * 65536 + (T & 1) * 128>(addr);
+    }
+    acc[0] ^= x[0].x ^ x[1].x; acc[0] ^= x[2].x ^ x[3].x;
+    acc[1] ^= x[0].y ^ x[1].y; acc[1] ^= x[2].y ^ x[3].y;
+    acc[2] ^= x[0].z ^ x[1].z; acc[2] ^= x[2].z ^ x[3].z;
+    acc[3] ^= x[0].w ^ x[1].w; acc[3] ^= x[2].w ^ x[3].w;
+}
+template <bool SEEDED>
+static __global__ void __launch_bounds__(ENC4_THREADS, 1) encrypt_tab4_kernel(Enc4Params p, const uint4 *__restrict__ table4) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t tbase = (s0 + 0xffffu) & ~0xffffu; // the host sizes the allocation for the worst-case alignment gap
+    {
+        uint32_t dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        if (tbase - s0 + ENC4_TABLE_BYTES > dyn) __trap();
+    }
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + (tbase - s0));
+        for (uint32_t i = tid; i < ENC4_TABLE_BYTES / 16; i += ENC4_THREADS) dst[i] = __ldg(table4 + i);
+    }
+    __syncthreads();
+    const uint32_t h = lane & 1, c = lane >> 1, r = c & 3;
+    uint32_t bb[4], sel[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t k = (r + s) & 3;      // class = byte k of the mask word = window group 4t + k
+        bb[s] = tbase + k * 32 + h * 16;     // bits 8..15 are zero: the mask byte goes there
+        sel[s] = 0x7604u | (k << 4);         // PRMT: byte 0, 2, 3 of the base, byte 1 <- byte k of the mask word
+    }
+    const uint32_t units = p.units;
+    const uint32_t nsuper = (units + 31u) / 32u;
+    const uint32_t gstride = gridDim.x * (ENC4_THREADS / 32);
+    for (uint32_t G = blockIdx.x * (ENC4_THREADS / 32) + warp; G < nsuper; G += gstride) {
+        uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+        uint4 mg[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if constexpr (SEEDED) {
+            const uint64_t gu = p.first_unit + (uint64_t)G * 32u + lane;
+            philox4x32_10((uint32_t)gu, (uint32_t)(gu >> 32), 0u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), rnd);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const uint32_t u = G * 32u + 16u * i + c;
+                if (u < units) mg[i] = __ldg(reinterpret_cast<const uint4 *>(p.masks) + u);
+            }
+        }
+        uint32_t pb[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t u = G * 32u + 16u * i + c;
+            pb[i] = (u < units) ? (uint32_t)__ldg(p.values + (u >> 3)) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t u = G * 32u + 16u * i + c;
+            uint32_t mk[4];
+            if constexpr (SEEDED) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) mk[w] = __shfl_sync(FULL, rnd[w], 16 * i + (int)c);
+            } else {
+                mk[0] = mg[i].x; mk[1] = mg[i].y; mk[2] = mg[i].z; mk[3] = mg[i].w;
+            }
+            if (u >= units) continue;
+            uint32_t acc[4] = {0u, 0u, 0u, 0u};
+            enc4_word<0>(mk[0], bb, sel, acc);
+            enc4_word<1>(mk[1], bb, sel, acc);
+            enc4_word<2>(mk[2], bb, sel, acc);
+            enc4_word<3>(mk[3], bb, sel, acc);
+            uint64_t *dst = p.out + (uint64_t)u * 5 + 2 * h;
+            if (h == 0) {
+                acc[0] ^= (pb[i] >> (u & 7)) & 1u; // + x (cipher.rs:112, polynomial.rs:238-243)
+            } else {
+                const uint32_t t = (mk[0] & p.topmask[0]) ^ (mk[1] & p.topmask[1]) ^ (mk[2] & p.topmask[2]) ^ (mk[3] & p.topmask[3]);
+                dst[2] = (uint64_t)(__popc(t) & 1);   // coefficient of X^256
+            }
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(acc[0], acc[1]);
+            *reinterpret_cast<uint2 *>(dst + 1) = make_uint2(acc[2], acc[3]);
+        }
+    }
+}
+
 // Generic path: any tau / D / window, table read from shared memory if it fits, else from L2.
 static __global__ void __launch_bounds__(256) encrypt_generic_kernel(EncParams p) {
     extern __shared__ __align__(16) uint64_t smem64[];

@@ -220,6 +220,12 @@ int hm_encrypt_seeded(hm_context *ctx, const uint8_t *values, size_t n, uint32_t
  * sync == 0 returns once the work is enqueued (see the *_async calls). */
 int hm_encrypt_seeded_at(hm_context *ctx, const uint8_t *values, size_t n, uint32_t L, uint64_t seed, uint64_t first_unit, int sync,
                          hm_batch **out);
+/* Seeded encryption of plaintexts already in HBM into an existing batch of n x L fresh-width slots (no allocation, no copy):
+ * the masks of stream positions [first_unit, first_unit + n L) are drawn inside the encrypt kernel where the parameter set
+ * has a fused kernel (d + d' = 256, tau = 128), else written to a temporary buffer first.  Same ciphertexts as
+ * hm_encrypt_device_into fed with hm_masks_generate_host(tau, ...). */
+int hm_encrypt_device_seeded_into(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, uint64_t seed, uint64_t first_unit,
+                                  hm_batch *out);
 /* Asynchronous forms of hm_encrypt / hm_decrypt: they return as soon as the copies and kernels are enqueued on the
  * context's stream.  The host buffers must stay valid (and, for decrypt, unread) until hm_context_synchronize; pinned
  * memory (hm_host_alloc) keeps the copies asynchronous.  They let one host thread drive several devices at once. */

@@ -48,3 +48,30 @@ def random_polys(rng, n, nwords, top_bits=64) -> np.ndarray:
     if top_bits < 64:
         a[:, -1] &= np.uint64((1 << top_bits) - 1)
     return a
+
+
+def philox_masks(units: int, seed: int, first_unit: int = 0, mask_bytes: int = 16) -> np.ndarray:
+    """The documented mask stream (include/hmgpu.h: Philox4x32-10, counter = (u_lo, u_hi, block, 0), key = seed), written
+    independently of the engine in numpy: bytes [16 b, 16 b + 16) of bit-ciphertext u, for u in [first_unit, first_unit + units)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    blocks = (mask_bytes + 15) // 16
+    u = np.repeat(np.arange(units, dtype=np.uint64) + np.uint64(first_unit), blocks)
+    c0 = (u & np.uint64(0xFFFFFFFF)).astype(np.uint64)
+    c1 = (u >> np.uint64(32)).astype(np.uint64)
+    c2 = np.tile(np.arange(blocks, dtype=np.uint64), units)
+    c3 = np.zeros_like(c0)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    mask32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(M0) * c0
+        p1 = np.uint64(M1) * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)
+        n1 = p1 & mask32
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)
+        n3 = p0 & mask32
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    words = np.stack([c0, c1, c2, c3], axis=1).astype("<u4")  # (units * blocks, 4)
+    by = words.view(np.uint8).reshape(units, blocks * 16)
+    return np.ascontiguousarray(by[:, :mask_bytes]).reshape(-1)

@@ -237,3 +237,22 @@ def test_shard_range_matches_the_python_rule():
     assert lib.hm_shard_range(10, 2, 2, C.byref(f), C.byref(c)) == N.HM_ERR_INVALID_ARGUMENT
     assert lib.hm_shard_range(10, 0, 0, C.byref(f), C.byref(c)) == N.HM_ERR_INVALID_ARGUMENT
     assert lib.hm_group_size(None) == 0 and lib.hm_group_create(128, 128, 1, 128, None, 0, None) == N.HM_ERR_INVALID_ARGUMENT
+
+
+def test_philox_stream_independent_restatement():
+    """The documented seeded-mask stream (include/hmgpu.h) computed by the library's host twin == a numpy restatement that
+    shares no code with it (tests/helpers.philox_masks) — the GPU tests use the latter to check stream positions > 0."""
+    import numpy as np
+
+    from helpers import philox_masks
+    from homomorph_rust_b200 import _native as N
+
+    lib = N.lib()
+    for tau, units, seed in ((128, 100, 12345678901234567), (200, 7, 99), (5, 9, 3), (256, 33, 2**64 - 1)):
+        mb = (tau + 7) // 8
+        out = np.zeros(units * mb, dtype=np.uint8)
+        assert lib.hm_masks_generate_host(tau, units, seed, out.ctypes.data) == 0
+        np.testing.assert_array_equal(philox_masks(units, seed, 0, mb), out)
+    # a later stream position is the tail of a longer stream from 0
+    full = philox_masks(50, 7, 0, 16)
+    np.testing.assert_array_equal(philox_masks(20, 7, 30, 16), full[30 * 16:])
