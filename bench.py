@@ -534,6 +534,36 @@ def run_ours(args, rank, local_rank, world):
             dt = float(np.median(times))
             extra[name] = {"value": n / dt, "unit": "u32/s", "ms": dt * 1e3, "ms_each": [round(x * 1e3, 3) for x in times]}
         del hv, hm_
+        # configs[1]: u32 batched encryption + decryption of 2^20 values, host plaintexts in -> ciphertexts in HBM -> host plaintexts
+        # out (Context::encrypt / Context::decrypt of benches/u32.rs on one batch); seeded masks, so 4 B per value cross PCIe each way
+        try:
+            n1 = 1 << 20
+            v1 = torch.from_numpy(np.random.default_rng(31).integers(0, 2**32, size=n1, dtype=np.uint32)).pin_memory()
+            r1 = torch.empty(n1, dtype=torch.int32).pin_memory()
+
+            def config1():
+                o = C.c_void_p()
+                assert lib.hm_encrypt_seeded(ctx._h, v1.data_ptr(), n1, L, 777, C.byref(o)) == 0
+                assert lib.hm_decrypt(ctx._h, o, r1.data_ptr()) == 0
+                lib.hm_batch_free(ctx._h, o)
+
+            config1(); ctx.synchronize()
+            t1s = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                config1()
+                ctx.synchronize()
+                t1s.append(time.perf_counter() - t0)
+            dt = float(np.median(t1s))
+            extra["config1_encrypt_decrypt"] = {"value": n1 / dt, "unit": "u32 round trips/s", "values": n1, "ms": dt * 1e3,
+                                                "ms_each": [round(x * 1e3, 3) for x in t1s],
+                                                "round_trip_exact": bool((r1.numpy().view(np.uint32) == v1.numpy()).all()),
+                                                "hbm_GBps": n1 * (1284 + 1284) / dt / 1e9,
+                                                "note": "configs[1]: hm_encrypt_seeded -> hm_decrypt through the C ABI with host plaintexts, wall clock incl. "
+                                                        "copies and the 1.34 GB batch allocation; 40 B written + 40 B read per bit-ciphertext"}
+            del v1, r1
+        except Exception as e:  # a secondary line must not take the headline down
+            extra["config1_encrypt_decrypt"] = {"error": repr(e)}
         # gates on fresh u32 batches (gate_xor / gate_and, common.rs:5-27): n*32 bit-ciphertext pairs per launch
         xo = ctx.apply2(hm.HomomorphicXorGate, ca, cb)
         s = timed(lambda: lib.hm_apply2_into(ctx._h, N.HM_OP_XOR, ca._h, cb._h, xo._h), reps=20)

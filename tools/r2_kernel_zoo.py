@@ -22,6 +22,13 @@ if cfg_b:
     for _ in range(2):
         assert lib.hm_poly_mulrem_into(ctx._h, ca._h, cb._h, mr._h) == 0
     ctx.synchronize()
+    # the fused D = 1024 adder chain on one exact wave of resident threads (2 CTAs x 128 threads per SM)
+    nw = 148 * 256
+    wa = rng.integers(0, 2**32, size=nw, dtype=np.uint32); wb = rng.integers(0, 2**32, size=nw, dtype=np.uint32)
+    xa, xb = ctx.encrypt(wa, seed=5), ctx.encrypt(wb, seed=6)
+    ws = ctx.apply2(hm.HomomorphicAddition, xa, xb)          # adder_chain_wide_kernel<2>
+    ctx.synchronize()
+    print("wide adder ok:", bool((ctx.decrypt(ws) == wa + wb).all()))
     print("zoo B done", ctx.kernel_launches())
     sys.exit(0)
 n, L = 1 << 18, 32
@@ -32,7 +39,8 @@ dv = torch.from_numpy(a.view(np.uint8).copy()).cuda()
 dout = torch.empty(n * 4, dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize()
 for _ in range(2):
-    assert lib.hm_encrypt_device_into(ctx._h, dv.data_ptr(), n, L, dm.data_ptr(), ca._h) == 0     # encrypt_tab6b_kernel
+    assert lib.hm_encrypt_device_into(ctx._h, dv.data_ptr(), n, L, dm.data_ptr(), ca._h) == 0     # encrypt_tab4_kernel<false> (HM_ENC_MODE=1: encrypt_tab6b_kernel)
+    assert lib.hm_encrypt_device_seeded_into(ctx._h, dv.data_ptr(), n, L, 12345, 0, ca._h) == 0    # encrypt_tab4_kernel<true> (Philox in the kernel)
     assert lib.hm_decrypt_device(ctx._h, ca._h, dout.data_ptr()) == 0                               # decrypt_uniform_kernel
 xo = ctx.apply2(hm.HomomorphicXorGate, ca, cb)                                                       # xor_flat_kernel
 ao = ctx.apply2(hm.HomomorphicAndGate, ca, cb)                                                       # mul_small_kernel<8,8>
