@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
         "hm_batch_upload": (C.c_int, [vp, sz, C.c_uint32, u32p, vp, C.POINTER(vp)]),
         "hm_batch_upload_bounded": (C.c_int, [vp, sz, C.c_uint32, u64p, vp, C.POINTER(vp)]),
         "hm_batch_download": (C.c_int, [vp, vp, vp]),
+        "hm_batch_download_range": (C.c_int, [vp, vp, sz, sz, vp]),
         "hm_batch_clone": (C.c_int, [vp, vp, C.POINTER(vp)]),
         "hm_batch_slice": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
         "hm_batch_concat": (C.c_int, [vp, C.POINTER(vp), C.c_size_t, C.POINTER(vp)]),

@@ -270,6 +270,12 @@ class Ciphered:
         _check(self._ctx._h, N.lib().hm_batch_download(self._ctx._h, self._h, out.ctypes.data))
         return out
 
+    def rows_to_host(self, first: int, count: int) -> np.ndarray:
+        """Values [first, first + count) only: (count, value_words) uint64."""
+        out = np.zeros((count, self.value_words), dtype=np.uint64)
+        _check(self._ctx._h, N.lib().hm_batch_download_range(self._ctx._h, self._h, first, count, out.ctypes.data))
+        return out
+
     def slot(self, host: np.ndarray, k: int) -> np.ndarray:
         w = self.slot_words()
         off = int(w[:k].sum())

@@ -1142,6 +1142,15 @@ int hm_batch_download(hm_context *ctx, const hm_batch *b, uint64_t *host) {
     return HM_OK;
 }
 
+int hm_batch_download_range(hm_context *ctx, const hm_batch *b, size_t first, size_t count, uint64_t *host) {
+    if (!ctx || !b || (!host && count)) return HM_ERR_INVALID_ARGUMENT;
+    if (first > b->n || count > b->n - first) return HM_ERR_INVALID_ARGUMENT;
+    USE_DEV(ctx);
+    if (count) CK(cudaMemcpyAsync(host, b->d + first * b->value_words, count * b->value_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HM_OK;
+}
+
 int hm_batch_clone(hm_context *ctx, const hm_batch *b, hm_batch **out) {
     if (!ctx || !b || !out) return HM_ERR_INVALID_ARGUMENT;
     USE_DEV(ctx);

@@ -141,6 +141,8 @@ void hm_batch_free(hm_context *ctx, hm_batch *b);
 int hm_batch_upload(hm_context *ctx, size_t n, uint32_t L, const uint32_t *slot_words, const uint64_t *host,
                     hm_batch **out);
 int hm_batch_download(hm_context *ctx, const hm_batch *b, uint64_t *host);
+/* Values [first, first + count) only (count * value_words words): spot checks and streaming readers of large results. */
+int hm_batch_download_range(hm_context *ctx, const hm_batch *b, size_t first, size_t count, uint64_t *host);
 /* Same as hm_batch_upload, but the caller states a degree bound per slot (>= the true degree of every
  * polynomial in that slot); slot k is degree_bounds[k]/64+1 words wide.  Tight bounds keep the results of
  * multiplications as narrow as the reference's (out len = (da+db)/64+1, src/polynomial.rs:264). */

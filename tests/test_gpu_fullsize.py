@@ -145,3 +145,36 @@ def test_config5_stress_mulrem_sweep(oracle, hm, log2n):
     np.testing.assert_array_equal(r_sum.to_host(), h_ab ^ r_cb.to_host())
     # and commutativity
     np.testing.assert_array_equal(ctx.poly_mulrem(cb, ca).to_host(), h_ab)
+
+
+def test_config_b_u32_add_one_wave(oracle, hm):
+    """Config B (d = d' = 512, tau = 256, delta = 8) u32 add on 37 888 + 40 pairs — above the dispatcher's switch to the fused
+    thread-per-value chain (adder_chain_wide_kernel), so this is the default path at that size: ONE launch; every slot of a
+    sample of values equals the oracle's add_internal (common.rs:37-56) word for word, all values decrypt to a + b, and the
+    result equals the regrouped generic plan's on a slice."""
+    sk, pk, skb, pkb = keys(oracle, *CONFIG_B, 105)
+    ctx = engine_context(hm, *CONFIG_B, skb, pkb)
+    n = 148 * 256 + 40
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    b = rng.integers(0, 2**32, size=n, dtype=np.uint32)
+    a[:3] = [0, 0xFFFFFFFF, 22]
+    b[:3] = [0, 1, 20]
+    ma, mb = rbytes(12, n * 32 * 32), rbytes(13, n * 32 * 32)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    l0 = ctx.kernel_launches()
+    s = ctx.apply2(hm.HomomorphicAddition, ca, cb)
+    assert ctx.kernel_launches() - l0 == 1
+    dec = ctx.decrypt(s)
+    np.testing.assert_array_equal(dec, a + b)  # d / delta = 64 >= 21: exact (operations.rs MIN_D_OVER_DELTA for u32 add)
+    idx = np.array([0, 1, 2, 31, 32, n // 2, n - 41, n - 1])
+    per = 32 * 32
+    oa = oracle_encrypt(oracle, pk, a[idx], ma.reshape(n, per)[idx].reshape(-1))
+    ob = oracle_encrypt(oracle, pk, b[idx], mb.reshape(n, per)[idx].reshape(-1))
+    want, _ = oracle.apply(oracle.OP_ADD, oa, ob, 32, threads=oracle.max_threads())
+    got = np.concatenate([s.rows_to_host(int(i), 1) for i in idx])
+    np.testing.assert_array_equal(got, expected_padded(want, len(idx), s.slot_words()))
+    m = 64
+    sa, sb = ctx.encrypt(a[:m], ma[: m * per]), ctx.encrypt(b[:m], mb[: m * per])
+    g = ctx.apply2(hm.HomomorphicAddition, sa, sb)  # 64 values: the regrouped generic plan
+    np.testing.assert_array_equal(g.to_host(), s.rows_to_host(0, m))
