@@ -93,7 +93,8 @@ struct hm_context {
     uint64_t *d_enc_table = nullptr;
     uint64_t *d_enc_table6 = nullptr; // bank-partitioned copy for encrypt_tab6_kernel (config A shape only)
     uint64_t *d_enc_table4 = nullptr; // four-class 32-byte-row copy for encrypt_tab4_kernel (config A shape only)
-    uint32_t enc_topmask[4] = {0, 0, 0, 0}; // bit i = coefficient of X^256 of T_i (the fifth word of a row, computed instead of looked up)
+    uint32_t enc_topmask[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // bit i = leading (X^D) coefficient of T_i: the last word of a row is computed, not looked up
+    uint64_t *d_enc_table4b = nullptr; // 128-byte-row copy for encrypt_tab4b_kernel (config B shape only)
 
     // ring of op descriptors: pinned host staging + device copy, so that launches need no host synchronisation
     MulOp *d_ops = nullptr;
@@ -339,6 +340,8 @@ void clear_public(hm_context *ctx) {
     if (ctx->d_enc_table6) cudaFree(ctx->d_enc_table6);
     if (ctx->d_enc_table4) cudaFree(ctx->d_enc_table4);
     ctx->d_enc_table4 = nullptr;
+    if (ctx->d_enc_table4b) cudaFree(ctx->d_enc_table4b);
+    ctx->d_enc_table4b = nullptr;
     for (uint32_t &m : ctx->enc_topmask) m = 0;
     ctx->d_enc_table = nullptr;
     ctx->d_enc_table6 = nullptr;
@@ -964,6 +967,21 @@ int hm_set_public_key(hm_context *ctx, const uint8_t *const *polys, const size_t
         CK(cudaMemcpyAsync(ctx->d_enc_table4, t4.data(), t4.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    if (in_smem && wb == 4 && wf == 17 && maxdeg == 1024 && tau == 256 && (size_t)hmk::ENC4B_TABLE_BYTES + 65536 + 1024 <= ctx->smem_optin) {
+        // encrypt_tab4b_kernel: words 0..15 of row (g, e) at byte (gp >> 4) * 65536 + (gp & 15) * 4096 + e * 256 + (g & 1) * 128, gp = g / 2
+        std::vector<uint64_t> t4((size_t)hmk::ENC4B_TABLE_BYTES / 8, 0);
+        for (uint32_t g = 0; g < groups; ++g)
+            for (uint32_t e = 0; e < 16; ++e) {
+                const uint32_t gp = g / 2;
+                const size_t byte = (size_t)(gp >> 4) * 65536 + (size_t)(gp & 15) * 4096 + (size_t)e * 256 + (g & 1) * 128;
+                for (uint32_t j = 0; j < 16; ++j) t4[byte / 8 + j] = tab[((size_t)(g << 4) + e) * 17 + j];
+            }
+        for (uint32_t i = 0; i < 256; ++i)
+            if (T[i].size() > 16 && (T[i][16] & 1)) ctx->enc_topmask[i / 32] |= 1u << (i % 32);
+        CK(cudaMalloc(&ctx->d_enc_table4b, t4.size() * 8));
+        CK(cudaMemcpyAsync(ctx->d_enc_table4b, t4.data(), t4.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->enc_wb = wb;
     ctx->enc_groups = groups;
     ctx->enc_table_words = (uint32_t)tab.size();
@@ -1389,7 +1407,7 @@ static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint
                         uint64_t first_unit = 0);
 static const int g_enc_mode = getenv("HM_ENC_MODE") ? atoi(getenv("HM_ENC_MODE")) : 2; // 2 = encrypt_tab4_kernel, 1 = encrypt_tab6(b)_kernel, 0 = encrypt_tab_kernel
 static bool encrypt_fuses_masks(const hm_context *ctx, uint64_t units) {
-    return g_enc_mode == 2 && ctx->d_enc_table4 && units < ((uint64_t)1 << 31);
+    return g_enc_mode == 2 && (ctx->d_enc_table4 || ctx->d_enc_table4b) && units < ((uint64_t)1 << 31);
 }
 
 int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
@@ -1427,6 +1445,28 @@ int hm_encrypt_device_into(hm_context *ctx, const uint8_t *d_values, size_t n, u
 static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks, hm_batch *b, uint64_t seed,
                         uint64_t first_unit) {
     if (n == 0) return HM_OK;
+    if (encrypt_fuses_masks(ctx, (uint64_t)n * L) && (!d_masks || ((uintptr_t)d_masks % 16) == 0) && ctx->d_enc_table4b) {
+        hmk::Enc4bParams q;
+        q.values = d_values;
+        q.masks = d_masks;
+        q.out = b->d;
+        q.units = (uint32_t)((uint64_t)n * L);
+        for (int i = 0; i < 8; ++i) q.topmask[i] = ctx->enc_topmask[i];
+        q.seed = seed;
+        q.first_unit = first_unit;
+        const size_t smem = (size_t)hmk::ENC4B_TABLE_BYTES + 65536;
+        const int grid = grid_for(ctx, ((uint64_t)q.units + 15) / 16 * 32, hmk::ENC4B_THREADS, 1);
+        const uint4 *t4 = reinterpret_cast<const uint4 *>(ctx->d_enc_table4b);
+        if (d_masks) {
+            CK(cudaFuncSetAttribute(hmk::encrypt_tab4b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hmk::encrypt_tab4b_kernel<false><<<grid, hmk::ENC4B_THREADS, smem, ctx->stream>>>(q, t4);
+        } else {
+            CK(cudaFuncSetAttribute(hmk::encrypt_tab4b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hmk::encrypt_tab4b_kernel<true><<<grid, hmk::ENC4B_THREADS, smem, ctx->stream>>>(q, t4);
+        }
+        LAUNCHED("encrypt_tab4b_kernel");
+        return HM_OK;
+    }
     if (encrypt_fuses_masks(ctx, (uint64_t)n * L) && (!d_masks || ((uintptr_t)d_masks % 16) == 0)) {
         hmk::Enc4Params q;
         q.values = d_values;

@@ -530,6 +530,116 @@ static __global__ void __launch_bounds__(ENC4_THREADS, 1) encrypt_tab4_kernel(En
     }
 }
 
+// The same design for the config-B shape (D = 1024, tau = 256): 128-byte rows (the coefficient of X^1024 is again computed as
+// parity(mask AND topmask)), 4-bit windows: 64 groups x 16 rows x 128 B = 128 KB.  EIGHT lanes per bit-ciphertext (16 bytes of the
+// row each): a quarter-warp reads one whole row per LDS.128 = all 32 banks once, conflict-free for any row; 4 ciphertexts per
+// warp pass, 64 lookups each.  Lines are again 256 B apart (the rows of an even group and the next odd group share a line)
+// and the table starts on a 64 KB boundary, so the address of a lookup is one PRMT on the mask word's even (or odd) nibbles.
+// SEEDED: every lane draws one 16-byte Philox block for the 16 ciphertexts of four passes; a pass fetches its 8 words by SHFL.
+// Replaces encrypt_tab_kernel<17,8,4,256> (thread per ciphertext, 136-byte rows at a 136-byte stride: bank conflicts on
+// every LDS.128, and a 32 B/bit mask buffer written and re-read).
+constexpr int ENC4B_THREADS = 1024;
+constexpr int ENC4B_TABLE_BYTES = 64 * 16 * 128;
+struct Enc4bParams {
+    const uint8_t *values;
+    const uint8_t *masks; // unused when SEEDED
+    uint64_t *out;
+    uint32_t units;
+    uint32_t topmask[8];
+    uint64_t seed, first_unit;
+};
+template <int GP> __device__ __forceinline__ void enc4b_pair(uint32_t ev, uint32_t od, uint32_t base, uint32_t sel, uint32_t (&acc)[4]) {
+    constexpr int IMM = (GP >> 4) * 65536 + (GP & 15) * 4096;
+    uint32_t ae, ao;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(ae) : "r"(ev), "r"(base), "r"(sel));
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(ao) : "r"(od), "r"(base), "r"(sel));
+    const uint4 x = lds128_off<IMM>(ae), y = lds128_off<IMM + 128>(ao);
+    acc[0] ^= x.x ^ y.x;
+    acc[1] ^= x.y ^ y.y;
+    acc[2] ^= x.z ^ y.z;
+    acc[3] ^= x.w ^ y.w;
+}
+template <int W> __device__ __forceinline__ void enc4b_word(uint32_t m, uint32_t base, const uint32_t (&sel)[4], uint32_t (&acc)[4]) {
+    const uint32_t ev = m & 0x0f0f0f0fu, od = (m >> 4) & 0x0f0f0f0fu; // even / odd window groups of this mask word, one per byte
+    enc4b_pair<4 * W + 0>(ev, od, base, sel[0], acc);
+    enc4b_pair<4 * W + 1>(ev, od, base, sel[1], acc);
+    enc4b_pair<4 * W + 2>(ev, od, base, sel[2], acc);
+    enc4b_pair<4 * W + 3>(ev, od, base, sel[3], acc);
+}
+template <bool SEEDED>
+static __global__ void __launch_bounds__(ENC4B_THREADS, 1) encrypt_tab4b_kernel(Enc4bParams p, const uint4 *__restrict__ table4b) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t tbase = (s0 + 0xffffu) & ~0xffffu;
+    {
+        uint32_t dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        if (tbase - s0 + ENC4B_TABLE_BYTES > dyn) __trap();
+    }
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + (tbase - s0));
+        for (uint32_t i = tid; i < ENC4B_TABLE_BYTES / 16; i += ENC4B_THREADS) dst[i] = __ldg(table4b + i);
+    }
+    __syncthreads();
+    const uint32_t j = lane & 7, q = lane >> 3;
+    const uint32_t base = tbase + 16 * j; // bits 8..15 are zero: the window value goes there
+    uint32_t sel[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sel[k] = 0x7604u | (k << 4);
+    const uint32_t units = p.units;
+    const uint32_t nsuper = (units + 15u) / 16u; // 16 ciphertexts = 4 passes per super-iteration
+    const uint32_t gstride = gridDim.x * (ENC4B_THREADS / 32);
+    for (uint32_t S = blockIdx.x * (ENC4B_THREADS / 32) + warp; S < nsuper; S += gstride) {
+        uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+        if constexpr (SEEDED) { // lane l: block (l & 1) of ciphertext 16 S + (l >> 1)
+            const uint64_t gu = p.first_unit + (uint64_t)S * 16u + (lane >> 1);
+            philox4x32_10((uint32_t)gu, (uint32_t)(gu >> 32), lane & 1, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), rnd);
+        }
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t u = S * 16u + 4u * i + q;
+            uint32_t mk[8];
+            if constexpr (SEEDED) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    mk[w] = __shfl_sync(FULL, rnd[w], 8 * i + 2 * (int)q);
+                    mk[4 + w] = __shfl_sync(FULL, rnd[w], 8 * i + 2 * (int)q + 1);
+                }
+            } else {
+                uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0;
+                if (u < units) {
+                    m0 = __ldg(reinterpret_cast<const uint4 *>(p.masks) + 2 * (uint64_t)u);
+                    m1 = __ldg(reinterpret_cast<const uint4 *>(p.masks) + 2 * (uint64_t)u + 1);
+                }
+                mk[0] = m0.x; mk[1] = m0.y; mk[2] = m0.z; mk[3] = m0.w;
+                mk[4] = m1.x; mk[5] = m1.y; mk[6] = m1.z; mk[7] = m1.w;
+            }
+            if (u >= units) continue;
+            const uint32_t pb = (uint32_t)__ldg(p.values + (u >> 3));
+            uint32_t acc[4] = {0u, 0u, 0u, 0u};
+            enc4b_word<0>(mk[0], base, sel, acc);
+            enc4b_word<1>(mk[1], base, sel, acc);
+            enc4b_word<2>(mk[2], base, sel, acc);
+            enc4b_word<3>(mk[3], base, sel, acc);
+            enc4b_word<4>(mk[4], base, sel, acc);
+            enc4b_word<5>(mk[5], base, sel, acc);
+            enc4b_word<6>(mk[6], base, sel, acc);
+            enc4b_word<7>(mk[7], base, sel, acc);
+            uint64_t *dst = p.out + (uint64_t)u * 17 + 2 * j;
+            if (j == 0) acc[0] ^= (pb >> (u & 7)) & 1u; // + x (cipher.rs:112)
+            if (j == 7) {
+                uint32_t t = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) t ^= mk[w] & p.topmask[w];
+                dst[2] = (uint64_t)(__popc(t) & 1); // coefficient of X^1024
+            }
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(acc[0], acc[1]);
+            *reinterpret_cast<uint2 *>(dst + 1) = make_uint2(acc[2], acc[3]);
+        }
+    }
+}
+
 // Generic path: any tau / D / window, table read from shared memory if it fits, else from L2.
 static __global__ void __launch_bounds__(256) encrypt_generic_kernel(EncParams p) {
     extern __shared__ __align__(16) uint64_t smem64[];

@@ -414,35 +414,39 @@ def test_encrypt_seeded_device_masks(oracle, hm, params, dtype, n):
         np.testing.assert_array_equal(ctx.decrypt(ct), values)
 
 
-@pytest.mark.parametrize("n,first_unit,odd_key", [(257, 0, False), (1, 5, False), (1031, (1 << 33) + 7, True), (40, 96, True)])
-def test_encrypt_fused_philox(oracle, hm, n, first_unit, odd_key):
-    """encrypt_tab4_kernel with the Philox masks drawn inside the kernel (hm_encrypt_device_seeded_into): equal, word for word, to
-    the oracle's cipher (cipher.rs:99-115) fed with the documented host stream from the same stream position, and to the
-    host-mask path of the same kernel.  odd_key: a public key whose polynomials do not all reach degree 256, so the computed
-    X^256 coefficient (parity of mask AND topmask) is exercised with a non-trivial topmask."""
+@pytest.mark.parametrize("params,n,first_unit,odd_key", [
+    (CONFIG_A, 257, 0, False), (CONFIG_A, 1, 5, False), (CONFIG_A, 1031, (1 << 33) + 7, True), (CONFIG_A, 40, 96, True),
+    (CONFIG_B, 131, 0, False), (CONFIG_B, 1, 3, True), (CONFIG_B, 517, (1 << 32) + 11, True)])
+def test_encrypt_fused_philox(oracle, hm, params, n, first_unit, odd_key):
+    """encrypt_tab4_kernel / encrypt_tab4b_kernel with the Philox masks drawn inside the kernel (hm_encrypt_device_seeded_into):
+    equal, word for word, to the oracle's cipher (cipher.rs:99-115) fed with the documented host stream from the same stream
+    position, and to the host-mask path of the same kernel.  odd_key: a public key whose polynomials do not all reach degree
+    d + d', so the computed leading coefficient (parity of mask AND topmask) is exercised with a non-trivial topmask."""
     import torch
 
     rng = np.random.default_rng(n)
-    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 91)
+    sk, pk, ctx = setup(oracle, hm, params, 91)
+    tau, wfull = params[3], (params[0] + params[1]) // 64
     if odd_key:
         polys = [pk.words(i).copy() for i in range(len(pk))]
         for i in range(0, len(polys), 3):  # every third polynomial loses its leading coefficient and a few more
-            polys[i] = polys[i][:4].copy()
-            polys[i][3] &= np.uint64((1 << (40 + i % 20)) - 1)
+            polys[i] = polys[i][:wfull].copy()
+            polys[i][wfull - 1] &= np.uint64((1 << (40 + i % 20)) - 1)
         pk = oracle.PolyVec.from_words(polys)
         ctx.set_public_key(hm.PublicKey.from_bytes([p.astype("<u8").tobytes() for p in polys]))
     L = 32
+    mbytes = tau // 8
     lib = hm.lib()
     values = rng.integers(0, 2**32, size=n, dtype=np.uint32)
     seed = 0xABCD_0000_1234 + n
-    out = ctx.encrypt(np.zeros(n, dtype=np.uint32), np.zeros(n * L * 16, dtype=np.uint8))
+    out = ctx.encrypt(np.zeros(n, dtype=np.uint32), np.zeros(n * L * mbytes, dtype=np.uint8))
     dv = torch.from_numpy(values.view(np.uint8).copy()).cuda()
     torch.cuda.synchronize()
     l0 = ctx.kernel_launches()
     assert lib.hm_encrypt_device_seeded_into(ctx._h, dv.data_ptr(), n, L, seed, first_unit, out._h) == 0
     ctx.synchronize()
     assert ctx.kernel_launches() - l0 == 1  # no mask_fill_kernel launch
-    masks = philox_masks(n * L, seed, first_unit)  # the documented stream, written independently in numpy
+    masks = philox_masks(n * L, seed, first_unit, mbytes)  # the documented stream, written independently in numpy
     if first_unit == 0:
         np.testing.assert_array_equal(masks, ctx.seeded_masks(n * L, seed))
     want = oracle_encrypt(oracle, pk, values, masks)

@@ -7,13 +7,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np, torch
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import homomorph_rust_b200 as hm
-    ctx = hm.Context(hm.Parameters(128, 128, 1, 128)); ctx.generate_keys_seeded(1)
+    cfg = (512, 512, 8, 256) if os.environ.get("ENC_AB_CFG") == "B" else (128, 128, 1, 128)
+    ctx = hm.Context(hm.Parameters(*cfg)); ctx.generate_keys_seeded(1)
     lib = hm.lib()
     n, L = 1 << 18, 32
     rng = np.random.default_rng(3)
     a = rng.integers(0, 2**32, size=n, dtype=np.uint32)
     dv = torch.from_numpy(a.view(np.uint8).copy()).cuda()
-    dm = torch.from_numpy(np.frombuffer(rng.bytes(n * L * 16), dtype=np.uint8).copy()).cuda()
+    dm = torch.from_numpy(np.frombuffer(rng.bytes(n * L * (cfg[3] // 8)), dtype=np.uint8).copy()).cuda()
     ce = ctx.encrypt(a, seed=1)
     def timed(fn, reps=20):
         fn(); ctx.synchronize()
@@ -35,6 +36,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(f"  masks in HBM {s1 * 1e6:7.1f} us ({n / s1 / 1e9:.2f} G u32/s)   seeded {s2 * 1e6:7.1f} us ({n / s2 / 1e9:.2f} G u32/s)   "
           f"seeded from host plaintexts {s3 * 1e6:7.1f} us ({n / s3 / 1e9:.2f} G u32/s)   decrypts back: {ok}", flush=True)
 else:
-    for mode, name in MODES.items():
-        print(f"HM_ENC_MODE={mode}: {name}", flush=True)
-        subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, HM_ENC_MODE=mode), check=False)
+    for cfg in ("A", "B"):
+        print(f"config {cfg} ({'d=dp=128, tau=128' if cfg == 'A' else 'd=dp=512, tau=256'}), 2^18 u32 = 8 388 608 bit-ciphertexts", flush=True)
+        for mode, name in MODES.items():
+            print(f" HM_ENC_MODE={mode}: {name if cfg == 'A' else name.replace('tab4_', 'tab4b_').replace('encrypt_tab6b_kernel', 'encrypt_tab_kernel<17,8,4,256>')}", flush=True)
+            subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, HM_ENC_MODE=mode, ENC_AB_CFG=cfg), check=False)
