@@ -22,6 +22,7 @@
 #include "gf2host.hpp"
 #include "kernels.cuh"
 #include "kernels_adder.h"
+#include "kernels_mul.h"
 #include "probes.h"
 
 namespace hmk {
@@ -34,6 +35,7 @@ static long g_adder_thread_min = -1;
 static long g_mul_thread_min = -1; // minimum (values x chunks) for the thread-per-chunk multiply; < 0 = default (128 per SM)
 static long g_mul_thread_chunk = 32; // 24 = the first thread-per-chunk kernel (3-way Karatsuba chunks)
 static long g_mul_circuit_seq = 0;
+static long g_mul_circuit_fused = getenv("HM_MUL_FUSED") ? atol(getenv("HM_MUL_FUSED")) : 1; // 1 = one-launch fused column multiplier where it applies (u8, D = 256)
 static long g_adder_chain = getenv("HM_ADDER_CHAIN") ? atol(getenv("HM_ADDER_CHAIN")) : 4;   // 0 = round-1 thread kernels; else 10 * (window in smem) + CTAs per SM
 static long g_adder_wide_min = getenv("HM_ADDER_WIDE_MIN") ? atol(getenv("HM_ADDER_WIDE_MIN")) : 0; // D = 1024 chain kernel from this many values on (0 = 256 per SM, < 0 = never)
 static long g_adder_phases = getenv("HM_ADDER_PHASES") ? atol(getenv("HM_ADDER_PHASES")) : 0; // work units per value of the scheduled adder chain; 0 = by batch size
@@ -105,6 +107,13 @@ struct hm_context {
     // work queue of the dynamically scheduled adder chain (kernels_adder.cu): counter + one flag per 32 values
     uint32_t *d_sched = nullptr;
     size_t sched_words = 0;
+
+    // fused column multiplier (kernels_mul.cu): the static plan for fresh u8 operands at D = 256, uploaded once
+    hmk::K7Plan k7_plan;
+    bool k7_ready = false;
+    hmk::K7Item *d_k7_items = nullptr;
+    hmk::K7Prod *d_k7_prods = nullptr;
+    hmk::K7Unit *d_k7_units = nullptr;
 
     cudaMemPool_t pool = nullptr;  // private stream-ordered pool: nothing process-wide is reconfigured
     cudaMemPool_t pool_big = nullptr; // second pool for batches above 1 GiB (results of circuits on big batches), so that small
@@ -765,6 +774,9 @@ void hm_context_destroy(hm_context *ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->d_k7_items) cudaFree(ctx->d_k7_items);
+    if (ctx->d_k7_prods) cudaFree(ctx->d_k7_prods);
+    if (ctx->d_k7_units) cudaFree(ctx->d_k7_units);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->pool_big) cudaMemPoolDestroy(ctx->pool_big);
     delete ctx;
@@ -812,6 +824,11 @@ int hm_set_tuning(const char *key, long value) {
     if (strcmp(key, "adder_chain") == 0) {
         if (value != 0 && value != 3 && value != 4 && value != 12 && value != 13) return HM_ERR_INVALID_ARGUMENT;
         g_adder_chain = value;
+        return HM_OK;
+    }
+    if (strcmp(key, "mul_circuit_fused") == 0) {
+        if (value != 0 && value != 1) return HM_ERR_INVALID_ARGUMENT;
+        g_mul_circuit_fused = value;
         return HM_OK;
     }
     if (strcmp(key, "adder_wide_min") == 0) {
@@ -2184,8 +2201,46 @@ static int mul_generic_seq(hm_context *ctx, const hm_batch *a, const hm_batch *b
 // (the same polynomials, bit for bit) are c_t = x_t * P_{t-1}: one prefix pass writes P_2..P_{m-1} and result[i] = P_m,
 // and the column's m-1 products are independent and go out as one batch of launches.  ~30 launches per u8 multiply
 // instead of ~180, and each product launch has enough (value, chunk) threads to fill the GPU.
+// One launch for the whole circuit (kernels_mul.cu) when both operands are fresh u8 batches at D = 256:
+// a warp per value, partial products, prefixes and carries in shared memory.  Returns HM_ERR_UNSUPPORTED when it does not apply.
+static int mul_fused(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
+    if (a->L != hmk::K7_L || ctx->fresh_deg != hmk::K7_D || !ctx->has_pk) return HM_ERR_UNSUPPORTED;
+    for (uint32_t k = 0; k < a->L; ++k)
+        if (a->degb[k] != hmk::K7_D || b->degb[k] != hmk::K7_D || a->w[k] != hmk::K7_D / 64 + 1 || b->w[k] != hmk::K7_D / 64 + 1) return HM_ERR_UNSUPPORTED;
+    hmk::K7Host host;
+    static const int k7_acc = getenv("HM_K7_ACC") ? atoi(getenv("HM_K7_ACC")) : 8;
+    if (!hmk::k7_build_plan(make_layout(o), o->degb.data(), (uint32_t)k7_acc, &host)) return HM_ERR_UNSUPPORTED;
+    static const int k7_warps = getenv("HM_K7_WARPS") ? atoi(getenv("HM_K7_WARPS")) : 8;
+    if (hmk::k7_smem_bytes(host.plan, k7_warps) > ctx->smem_optin) return HM_ERR_UNSUPPORTED;
+    if (!ctx->k7_ready || memcmp(&ctx->k7_plan, &host.plan, sizeof(hmk::K7Plan)) != 0) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->k7_ready = false;
+        if (ctx->d_k7_items) cudaFree(ctx->d_k7_items);
+        if (ctx->d_k7_prods) cudaFree(ctx->d_k7_prods);
+        if (ctx->d_k7_units) cudaFree(ctx->d_k7_units);
+        ctx->d_k7_items = nullptr;
+        ctx->d_k7_prods = nullptr;
+        ctx->d_k7_units = nullptr;
+        CK(cudaMalloc(&ctx->d_k7_items, host.items.size() * sizeof(hmk::K7Item)));
+        CK(cudaMalloc(&ctx->d_k7_prods, host.prods.size() * sizeof(hmk::K7Prod)));
+        CK(cudaMalloc(&ctx->d_k7_units, host.units.size() * sizeof(hmk::K7Unit)));
+        CK(cudaMemcpy(ctx->d_k7_items, host.items.data(), host.items.size() * sizeof(hmk::K7Item), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_k7_prods, host.prods.data(), host.prods.size() * sizeof(hmk::K7Prod), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_k7_units, host.units.data(), host.units.size() * sizeof(hmk::K7Unit), cudaMemcpyHostToDevice));
+        memcpy(&ctx->k7_plan, &host.plan, sizeof(hmk::K7Plan));
+        ctx->k7_ready = true;
+    }
+    CK(hmk::launch_mul_circuit_fused(k7_warps, a->d, b->d, o->d, a->n, o->value_words, ctx->k7_plan, ctx->d_k7_items, ctx->d_k7_prods, ctx->d_k7_units,
+                                     ctx->sm_count, ctx->stream));
+    return post_launch(ctx, "mul_circuit_fused_kernel");
+}
+
 static int mul_generic(hm_context *ctx, const hm_batch *a, const hm_batch *b, hm_batch *o) {
     if (g_mul_circuit_seq) return mul_generic_seq(ctx, a, b, o);
+    if (g_mul_circuit_fused) {
+        const int rcf = mul_fused(ctx, a, b, o);
+        if (rcf != HM_ERR_UNSUPPORTED) return rcf;
+    }
     const uint32_t L = a->L;
     const size_t n = a->n;
     struct Obj {

@@ -543,16 +543,54 @@ def test_mul_circuit_plans_agree(oracle, hm, force_thread):
         assert lib.hm_set_tuning(b"mul_circuit_sequential", 1) == 0
         seq = ctx.apply2(hm.HomomorphicMultiplication, ca, cb).to_host()
         assert lib.hm_set_tuning(b"mul_circuit_sequential", 0) == 0
+        assert lib.hm_set_tuning(b"mul_circuit_fused", 0) == 0
+        l0 = ctx.kernel_launches()
         r = ctx.apply2(hm.HomomorphicMultiplication, ca, cb)
+        assert ctx.kernel_launches() - l0 > 1  # the column-batched plan
+        assert lib.hm_set_tuning(b"mul_circuit_fused", 1) == 0
+        l0 = ctx.kernel_launches()
+        fused = ctx.apply2(hm.HomomorphicMultiplication, ca, cb)
+        assert ctx.kernel_launches() - l0 == 1  # the fused column multiplier (kernels_mul.cu)
     finally:
         lib.hm_set_tuning(b"mul_thread_min", -1)
         lib.hm_set_tuning(b"mul_thread_chunk", 32)
         lib.hm_set_tuning(b"mul_circuit_sequential", 0)
+        lib.hm_set_tuning(b"mul_circuit_fused", 1)
     np.testing.assert_array_equal(r.to_host(), seq)
+    np.testing.assert_array_equal(fused.to_host(), seq)
     oa, ob = oracle_encrypt(oracle, pk, a, ma), oracle_encrypt(oracle, pk, b, mb)
     want, _ = oracle.apply(oracle.OP_MUL, oa, ob, L, threads=oracle.max_threads())
     np.testing.assert_array_equal(r.to_host(), expected_padded(want, n, r.slot_words()))
     np.testing.assert_array_equal(ctx.decrypt(r), a * b)
+
+
+@pytest.mark.parametrize("dtype,n", [(np.uint8, 1), (np.uint8, 9), (np.int8, 300), (np.uint8, 1300)])
+def test_mul_fused_column_multiplier(oracle, hm, dtype, n):
+    """The one-launch fused column multiplier (a warp per value, partial products, prefixes and carries in
+    shared memory) on ragged batch sizes — fewer values than warps in a CTA, more than one CTA per SM's worth — against the
+    oracle's mul_unsigned_internal / mul_signed_internal (common.rs:66-155), every slot word for word."""
+    rng = np.random.default_rng(n)
+    sk, pk, ctx = setup(oracle, hm, CONFIG_A, 57)
+    L = 8
+    info = np.iinfo(dtype)
+    a = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+    b = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+    a[:1] = [info.max]
+    b[:1] = [info.max]
+    ma, mb = masks_for(rng, n, L, 128), masks_for(rng, n, L, 128)
+    ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
+    l0 = ctx.kernel_launches()
+    r = ctx.apply2(hm.HomomorphicMultiplication, ca, cb)
+    assert ctx.kernel_launches() - l0 == 1
+    k = min(n, 48)
+    oa, ob = oracle_encrypt(oracle, pk, a[:k].view(np.uint8), ma[: k * L * 16]), oracle_encrypt(oracle, pk, b[:k].view(np.uint8), mb[: k * L * 16])
+    want, _ = oracle.apply(oracle.OP_MUL_SIGNED if info.min < 0 else oracle.OP_MUL, oa, ob, L, threads=oracle.max_threads())
+    np.testing.assert_array_equal(r.to_host()[:k], expected_padded(want, k, r.slot_words()))
+    with np.errstate(over="ignore"):
+        np.testing.assert_array_equal(ctx.decrypt(r), (a * b).astype(dtype))
+    # a second batch through the same context reuses the uploaded plan
+    r2 = ctx.apply2(hm.HomomorphicMultiplication, cb, ca)
+    np.testing.assert_array_equal(ctx.decrypt(r2), ctx.decrypt(r))
 
 
 @pytest.mark.parametrize("params", [(64, 32, 1, 32), CONFIG_A])
