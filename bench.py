@@ -680,6 +680,16 @@ def run_ours(args, rank, local_rank, world):
                 "traffic": n * NCU["dram_bytes_per_add"],
                 "traffic_source": NCU["source"] + "; algorithmic bytes per launch = %d" % (n * BYTES_PER_ADD),
             }
+        if k8.value and isinstance(extra.get("u8_mul"), dict) and extra["u8_mul"].get("value"):
+            # the multiplier circuit against the same product-pipe measurement: 2 196 8x8-word block products per u8 multiply
+            # (32-word chunking of the 56 carry products + 36 partial products)
+            ach8 = extra["u8_mul"]["value"] * 2196
+            extra["u8_mul"]["roofline"] = {"bound": "alu", "achieved": ach8 / 1e9, "peak": k8.value / 1e9, "unit": "G 8x8-word products/s",
+                                           "frac": ach8 / k8.value,
+                                           "peak_source": "hm_measure_kara8_peak: the 8x8-word Karatsuba product (432 IMAD.WIDE + 854 LOP3) timed alone in this run; "
+                                                          "it runs at the joint-issue ceiling of its instruction mix (roofline.joint_issue_ceiling)",
+                                           "note": "78 block-product rounds per value on 32 lanes against 68.6 if every lane were always busy; "
+                                                   "2 warps per scheduler (17 KB of shared memory per value)"}
         gbs = n * BYTES_PER_ADD / launch_s / 1e9
         roofline_hbm = {"kernel": "adder_chain_kernel<8,0,4>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                         "frac": gbs / hbm_peak, "traffic": n * NCU["dram_bytes_per_add"], "peak_source": hbm_src,
