@@ -689,7 +689,7 @@ def run_ours(args, rank, local_rank, world):
                                            "peak_source": "hm_measure_kara8_peak: the 8x8-word Karatsuba product (432 IMAD.WIDE + 854 LOP3) timed alone in this run; "
                                                           "it runs at the joint-issue ceiling of its instruction mix (roofline.joint_issue_ceiling)",
                                            "note": "78 block-product rounds per value on 32 lanes against 68.6 if every lane were always busy; "
-                                                   "2 warps per scheduler (17 KB of shared memory per value)"}
+                                                   "2 warps per scheduler (25 KB of shared memory per value)"}
         gbs = n * BYTES_PER_ADD / launch_s / 1e9
         roofline_hbm = {"kernel": "adder_chain_kernel<8,0,4>", "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                         "frac": gbs / hbm_peak, "traffic": n * NCU["dram_bytes_per_add"], "peak_source": hbm_src,
