@@ -2,7 +2,7 @@
 // (mul_unsigned_internal) for u8 operands of fresh ciphertexts at D = d + d' = 256, ONE launch for the whole circuit.
 //
 // One WARP per value; everything the circuit produces on the way — the 36 partial products, the column prefixes and the
-// 56 carries — lives in the warp's 23 KB slice of shared memory, so HBM sees the 2 x 320 B of operands and the 4.2 KB
+// 56 carries — lives in the warp's 25 KB slice of shared memory, so HBM sees the 2 x 320 B of operands and the 4.2 KB
 // result and nothing else (the column-batched plan of hmgpu.cu moves a 32 KB arena per value through HBM in 24 launches).
 //
 // The circuit, column by column (the same regrouping as the host plan, so the same canonical polynomials): in column i
