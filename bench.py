@@ -463,6 +463,29 @@ def run_ours(args, rank, local_rank, world):
                                     "note": "configs[4]: carry-less mul + rem sweep; operands reduced mod S first (sliding-window table folds from shared "
                                             "memory), then a 16-word product (three 8x8-word Karatsubas) and one more fold; aggregate over ranks, "
                                             "small batches are launch-latency bound"}
+        if rank == 0:
+            # config-B encryption on the tensor cores: 2^22 bit-ciphertexts (the sweep's largest operand) encrypted again in place
+            try:
+                dvb = torch.from_numpy(vb1.copy()).to(dev)
+                torch.cuda.synchronize()
+
+                def enc_b():
+                    assert lib.hm_encrypt_device_seeded_into(ctxb._h, dvb.data_ptr(), nb, 8, 77 + rank, 0, cb1._h) == 0
+
+                sb = timed(enc_b, reps=10, strm=streamb, sync=ctxb.synchronize)
+                units_b = nb * 8
+                extra["encrypt_config_b"] = {"value": units_b / sb, "unit": "bit-ciphertexts/s", "ms": sb * 1e3, "units": units_b,
+                                             "kernel": "encrypt_umma_b_kernel<true> x 2 passes (tcgen05.mma kind::i8, M128 N256 K32; accumulators in TMEM; "
+                                                       "parity-and-pack epilogue; Philox masks drawn in the kernel)",
+                                             "hbm_GBps": units_b * 136 / sb / 1e9,
+                                             "tensor": {"int8_MAC_per_s": units_b * 256 * 1024 / sb,
+                                                        "frac_of_probe_rate": (units_b * 256 * 1024 / sb) / (128 * 256 * 128 / 4.9 * 148 * 1.965e9),
+                                                        "note": "against the MMA-only stream of tools/umma_encrypt_probe.cu (4.9 clk per 128x256x128 tile per SM)"},
+                                             "note": "masks[n x 256] * PK[256 x 1025] over GF(2) as an int8 GEMM; the table kernel encrypt_tab4b_kernel takes "
+                                                     "1.48x as long (HM_ENC_MODE=2)"}
+                del dvb
+            except Exception as e:
+                extra["encrypt_config_b"] = {"error": repr(e)}
         for ob in (cb1, cb2):
             ob.free()
         ctxb.close()

@@ -31,7 +31,7 @@ HM_OP_AND, HM_OP_OR, HM_OP_XOR, HM_OP_NOT, HM_OP_ADD, HM_OP_MUL = range(6)
 
 def build(force: bool = False) -> str:
     """Compile csrc/ into libhmgpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("hmgpu.cu", "kernels_b.cu", "kernels_adder.cu", "kernels_adder.h", "kernels_mul.cu", "kernels_mul.h", "probes.cu", "probes.h", "hmgroup.cu", "kernels.cuh", "gf2_blocks.cuh", "gf2host.hpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("hmgpu.cu", "kernels_b.cu", "kernels_adder.cu", "kernels_adder.h", "kernels_mul.cu", "kernels_mul.h", "kernels_enc_umma.cu", "kernels_enc_umma.h", "probes.cu", "probes.h", "hmgroup.cu", "kernels.cuh", "gf2_blocks.cuh", "gf2host.hpp")]
     srcs.append(os.path.join(_HERE, "..", "include", "hmgpu.h"))
     stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
     if force or stale:

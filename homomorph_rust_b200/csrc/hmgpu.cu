@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "kernels_adder.h"
 #include "kernels_mul.h"
+#include "kernels_enc_umma.h"
 #include "probes.h"
 
 namespace hmk {
@@ -97,6 +98,7 @@ struct hm_context {
     uint64_t *d_enc_table4 = nullptr; // four-class 32-byte-row copy for encrypt_tab4_kernel (config A shape only)
     uint32_t enc_topmask[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // bit i = leading (X^D) coefficient of T_i: the last word of a row is computed, not looked up
     uint64_t *d_enc_table4b = nullptr; // 128-byte-row copy for encrypt_tab4b_kernel (config B shape only)
+    int8_t *d_enc_umma = nullptr;      // B operand of the tensor-core encrypt kernel (config B shape only)
 
     // ring of op descriptors: pinned host staging + device copy, so that launches need no host synchronisation
     MulOp *d_ops = nullptr;
@@ -351,6 +353,8 @@ void clear_public(hm_context *ctx) {
     ctx->d_enc_table4 = nullptr;
     if (ctx->d_enc_table4b) cudaFree(ctx->d_enc_table4b);
     ctx->d_enc_table4b = nullptr;
+    if (ctx->d_enc_umma) cudaFree(ctx->d_enc_umma);
+    ctx->d_enc_umma = nullptr;
     for (uint32_t &m : ctx->enc_topmask) m = 0;
     ctx->d_enc_table = nullptr;
     ctx->d_enc_table6 = nullptr;
@@ -998,6 +1002,18 @@ int hm_set_public_key(hm_context *ctx, const uint8_t *const *polys, const size_t
         CK(cudaMalloc(&ctx->d_enc_table4b, t4.size() * 8));
         CK(cudaMemcpyAsync(ctx->d_enc_table4b, t4.data(), t4.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        { // the same key as the int8 B operand of encrypt_umma_b_kernel (2 x 128 KB)
+            std::vector<const uint64_t *> tp(256);
+            std::vector<size_t> tw(256);
+            for (uint32_t i = 0; i < 256; ++i) {
+                tp[i] = T[i].data();
+                tw[i] = T[i].size();
+            }
+            std::vector<int8_t> bt(hmk::enc_umma_table_bytes());
+            hmk::enc_umma_build_table(tp.data(), tw.data(), bt.data());
+            CK(cudaMalloc(&ctx->d_enc_umma, bt.size()));
+            CK(cudaMemcpy(ctx->d_enc_umma, bt.data(), bt.size(), cudaMemcpyHostToDevice));
+        }
     }
     ctx->enc_wb = wb;
     ctx->enc_groups = groups;
@@ -1422,9 +1438,9 @@ void hm_host_free(void *p) {
 // encrypt_fuses_masks(ctx, n * L) says so)
 static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks, hm_batch *b, uint64_t seed = 0,
                         uint64_t first_unit = 0);
-static const int g_enc_mode = getenv("HM_ENC_MODE") ? atoi(getenv("HM_ENC_MODE")) : 2; // 2 = encrypt_tab4_kernel, 1 = encrypt_tab6(b)_kernel, 0 = encrypt_tab_kernel
+static const int g_enc_mode = getenv("HM_ENC_MODE") ? atoi(getenv("HM_ENC_MODE")) : 3; // 3 = encrypt_tab4_kernel at config A, tensor-core encrypt_umma_b_kernel at config B; 2 = encrypt_tab4(b)_kernel; 1 = encrypt_tab6(b)_kernel; 0 = encrypt_tab_kernel
 static bool encrypt_fuses_masks(const hm_context *ctx, uint64_t units) {
-    return g_enc_mode == 2 && (ctx->d_enc_table4 || ctx->d_enc_table4b) && units < ((uint64_t)1 << 31);
+    return g_enc_mode >= 2 && (ctx->d_enc_table4 || ctx->d_enc_table4b) && units < ((uint64_t)1 << 31);
 }
 
 int hm_encrypt_device(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks,
@@ -1462,6 +1478,21 @@ int hm_encrypt_device_into(hm_context *ctx, const uint8_t *d_values, size_t n, u
 static int encrypt_exec(hm_context *ctx, const uint8_t *d_values, size_t n, uint32_t L, const uint8_t *d_masks, hm_batch *b, uint64_t seed,
                         uint64_t first_unit) {
     if (n == 0) return HM_OK;
+    if (g_enc_mode == 3 && encrypt_fuses_masks(ctx, (uint64_t)n * L) && (!d_masks || ((uintptr_t)d_masks % 16) == 0) && ctx->d_enc_umma) {
+        hmk::EncUmmaParams q;
+        q.values = d_values;
+        q.masks = d_masks;
+        q.out = b->d;
+        q.units = (uint32_t)((uint64_t)n * L);
+        static const int umma_chunk = getenv("HM_UMMA_CHUNK") ? atoi(getenv("HM_UMMA_CHUNK")) : 0;
+        q.chunk_tiles = (uint32_t)umma_chunk;
+        for (int i = 0; i < 8; ++i) q.topmask[i] = ctx->enc_topmask[i];
+        q.seed = seed;
+        q.first_unit = first_unit;
+        CK(hmk::launch_encrypt_umma_b(q, d_masks == nullptr, ctx->d_enc_umma, ctx->sm_count, ctx->stream));
+        LAUNCHED("encrypt_umma_b_kernel");
+        return HM_OK;
+    }
     if (encrypt_fuses_masks(ctx, (uint64_t)n * L) && (!d_masks || ((uintptr_t)d_masks % 16) == 0) && ctx->d_enc_table4b) {
         hmk::Enc4bParams q;
         q.values = d_values;

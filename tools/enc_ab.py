@@ -1,7 +1,7 @@
 """Config A encryption kernels side by side (HM_ENC_MODE is read once per process, so each mode runs in its own process):
 device-timed encrypt with masks in HBM, seeded encrypt (masks from Philox), and seeded end to end from host plaintexts."""
 import os, subprocess, sys, time
-MODES = {"2": "encrypt_tab4_kernel (+ Philox in the kernel)", "1": "encrypt_tab6b_kernel + mask_fill_kernel"}
+MODES = {"3": "tensor cores at config B: encrypt_umma_b_kernel (tcgen05 kind::i8, one launch); config A as mode 2", "2": "encrypt_tab4_kernel (+ Philox in the kernel)", "1": "encrypt_tab6b_kernel + mask_fill_kernel"}
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import ctypes as C
     import numpy as np, torch

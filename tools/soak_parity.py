@@ -110,7 +110,7 @@ a = rng.integers(0, 256, size=n, dtype=np.uint8); b = rng.integers(0, 256, size=
 ma, mb = rb(11, n * 8 * 32), rb(12, n * 8 * 32)
 ca, cb = ctx.encrypt(a, ma), ctx.encrypt(b, mb)
 oa, ob = oracle_encrypt(orc, pk, a, ma), oracle_encrypt(orc, pk, b, mb)
-check("config B: encrypt u8 (4-bit-window table kernel)", ca.to_host(), expected_padded(oa, n, [17] * 8), t0)
+check("config B: encrypt u8 (tensor-core encrypt_umma_b_kernel, host masks)", ca.to_host(), expected_padded(oa, n, [17] * 8), t0)
 check("config B: decrypt fresh u8", ctx.decrypt(ca), orc.decrypt(sk, oa, 8, threads=T)[0], t0)
 r = ctx.poly_mulrem(ca, cb)
 wr, _ = orc.poly_mulrem(oa, ob, sk, threads=T)
@@ -130,7 +130,7 @@ for batch, vals, seed, fu in ((ea, a, 5 + SEED, 7), (eb, b, 6 + SEED, 9)):
     dv = torch.from_numpy(vals.view(np.uint8).copy()).cuda(); torch.cuda.synchronize()
     assert lib.hm_encrypt_device_seeded_into(ctx._h, dv.data_ptr(), n, 32, seed, fu, batch._h) == 0
 oa, ob = oracle_encrypt(orc, pk, a, ma), oracle_encrypt(orc, pk, b, mb)
-check("config B: seeded encrypt u32 (encrypt_tab4b_kernel)", ea.to_host(), expected_padded(oa, n, [17] * 32), t0)
+check("config B: seeded encrypt u32 (tensor-core encrypt_umma_b_kernel)", ea.to_host(), expected_padded(oa, n, [17] * 32), t0)
 lib.hm_set_tuning(b"adder_wide_min", 1)
 s = ctx.apply2(hm.HomomorphicAddition, ea, eb)
 lib.hm_set_tuning(b"adder_wide_min", 0)
