@@ -479,10 +479,10 @@ def run_ours(args, rank, local_rank, world):
                                                        "parity-and-pack epilogue; Philox masks drawn in the kernel)",
                                              "hbm_GBps": units_b * 136 / sb / 1e9,
                                              "tensor": {"int8_MAC_per_s": units_b * 256 * 1024 / sb,
-                                                        "frac_of_probe_rate": (units_b * 256 * 1024 / sb) / (128 * 256 * 128 / 4.9 * 148 * 1.965e9),
-                                                        "note": "against the MMA-only stream of tools/umma_encrypt_probe.cu (4.9 clk per 128x256x128 tile per SM)"},
+                                                        "frac_of_probe_rate": (units_b * 256 * 1024 / sb) / (256 * 128 / 4.9 * 148 * 1.965e9),
+                                                        "note": "against the MMA-only stream of tools/umma_encrypt_probe.cu (4.9 clk per bit-ciphertext of a 128x256x128 tile per SM = 6.7 k int8 MAC per clk per SM)"},
                                              "note": "masks[n x 256] * PK[256 x 1025] over GF(2) as an int8 GEMM; the table kernel encrypt_tab4b_kernel takes "
-                                                     "1.48x as long (HM_ENC_MODE=2)"}
+                                                     "1.47x as long (HM_ENC_MODE=2)"}
                 del dvb
             except Exception as e:
                 extra["encrypt_config_b"] = {"error": repr(e)}
