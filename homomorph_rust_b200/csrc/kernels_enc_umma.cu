@@ -28,6 +28,7 @@ namespace {
 constexpr int TILE_M = 128, BLK_N = 256, K = 256;
 constexpr uint32_t LBO = 128, SBO = (K / 16) * 128;                 // core matrix = 8 rows x 16 B, K-adjacent cores contiguous
 constexpr uint32_t A_BYTES = TILE_M * K, B_BYTES = ENC_UMMA_PASS_COLS * K;
+constexpr int A_STAGES = 2; // A tiles in flight (3 fit as well and change nothing: the producers are not what the tensor pipe waits for)
 constexpr int EPI_WARPS = 16, PROD_WARPS = 4, THREADS = (EPI_WARPS + PROD_WARPS + 1) * 32;
 // kind::i8: D = S32 (2 << 4), A and B signed 8 bit (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLK_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
@@ -99,14 +100,16 @@ __device__ __forceinline__ void philox(uint32_t c0, uint32_t c1, uint32_t c2, ui
 template <bool SEEDED>
 __global__ void __launch_bounds__(THREADS, 1) encrypt_umma_b_kernel(EncUmmaParams p, const uint4 *__restrict__ Bg) {
     extern __shared__ __align__(1024) uint8_t umma_smem[];
-    uint8_t *sB = umma_smem, *sA = umma_smem + B_BYTES; // B half, then two A buffers
-    __shared__ __align__(8) uint64_t a_full[2], a_empty[2], d_full[2], d_empty[2];
+    uint8_t *sB = umma_smem, *sA = umma_smem + B_BYTES; // B half, then the A buffers
+    __shared__ __align__(8) uint64_t a_full[A_STAGES], a_empty[A_STAGES], d_full[2], d_empty[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < A_STAGES; ++s) {
             mbar_init(&a_full[s], PROD_WARPS * 32);
             mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(&d_full[s], 1);
             mbar_init(&d_empty[s], EPI_WARPS * 32);
         }
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, 1) encrypt_umma_b_kernel(EncUmmaParam
         uint32_t it = it0;
         for (uint32_t ti = c0; ti < c1; ++ti, ++it) {
             const uint32_t tile = blockIdx.x + ti * gridDim.x;
-            const uint32_t s = it & 1, u = tile * TILE_M + row;
+            const uint32_t s = it % A_STAGES, u = tile * TILE_M + row;
             uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
             if (u < p.units) {
                 if constexpr (SEEDED) {
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(THREADS, 1) encrypt_umma_b_kernel(EncUmmaParam
                     p.out[(uint64_t)u * 17 + 16] = (uint64_t)(__popc(t) & 1);
                 }
             }
-            mbar_wait(&a_empty[s], ((it >> 1) & 1) ^ 1); // the MMAs that read this buffer two tiles ago are complete
+            mbar_wait(&a_empty[s], ((it / A_STAGES) & 1) ^ 1); // the MMAs that read this buffer A_STAGES tiles ago are complete
             uint8_t *arow = sA + s * A_BYTES + (row >> 3) * SBO + (row & 7) * 16;
 #pragma unroll
             for (int kc = 0; kc < K / 16; ++kc) { // 16 mask bits -> one 16-byte row of a core matrix
@@ -218,8 +221,8 @@ __global__ void __launch_bounds__(THREADS, 1) encrypt_umma_b_kernel(EncUmmaParam
         const uint64_t bdesc = make_desc(smem_u32(sB));
         uint32_t it = it0;
         for (uint32_t ti = c0; ti < c1; ++ti, ++it) {
-            const uint32_t s = it & 1;
-            mbar_wait(&a_full[s], (it >> 1) & 1);
+            const uint32_t s = it % A_STAGES;
+            mbar_wait(&a_full[s], (it / A_STAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t adesc = make_desc(smem_u32(sA + s * A_BYTES));
 #pragma unroll 1
@@ -261,7 +264,7 @@ void enc_umma_build_table(const uint64_t *const *T, const size_t *T_words, int8_
 }
 
 cudaError_t launch_encrypt_umma_b(const EncUmmaParams &p0, bool seeded, const int8_t *d_table, int sm_count, cudaStream_t stream) {
-    const size_t smem = (size_t)B_BYTES + 2 * A_BYTES + 1024;
+    const size_t smem = (size_t)B_BYTES + A_STAGES * A_BYTES + 1024;
     auto kern = seeded ? encrypt_umma_b_kernel<true> : encrypt_umma_b_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
